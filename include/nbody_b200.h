@@ -1,0 +1,192 @@
+/*
+ * nbody_b200.h -- C ABI of the B200-native N-body engine (libnbody_b200.so).
+ *
+ * This is the drop-in boundary for the particle-simulation hot path of
+ * matty9090/Procedural-Universe (src/Sim).  The reference has no FFI of its own: its sims sit
+ * behind the C++ interface
+ *
+ *     class INBodySim { virtual void Init(std::vector<Particle>&); virtual void Update(float dt); }
+ *                                                     (reference src/Sim/INBodySim.hpp:19-25)
+ *     class IParticleSeeder { virtual void Seed(uint64_t seed); }
+ *                                                     (reference src/Sim/IParticleSeeder.hpp:19-27)
+ *
+ * Every entry point below names the reference member it stands in for.  The C++ adapter
+ * `B200Sim : INBodySim` (procedural-universe_b200/host/B200Sim.hpp) is a ~100-line wrapper over
+ * exactly these calls; INTEGRATION.md shows the factory patch a maintainer would add.
+ *
+ * Conventions
+ *   - plain C, POD arguments only; every function returns NB_OK (0) or a negative nb_status and
+ *     leaves a message for nb_last_error() (the reference's sims return void and log failures,
+ *     BruteForceGPU.cpp:25-33; the adapter turns a non-zero status into LOGE and keeps the last
+ *     good state);
+ *   - a handle is driven by one host thread at a time (the reference calls Update from the UI
+ *     thread only, SimulationState.cpp:52-53);
+ *   - there is NO CPU fallback: with no CUDA device or with a kernel image that does not match the
+ *     device (sm_100a only) nb_create fails with NB_ERR_CUDA.
+ *
+ * Particle record (reference src/Render/Misc/Particle.hpp:8-18, g++/MSVC x64 layout, 104 bytes):
+ *   Position float3 @0 | Colour float4 @12 | OriginalColour float4 @28 | pad @44 |
+ *   Velocity double3 @48 | Forces double3 @72 | Mass double @96
+ * The engine reads Position, Velocity and Mass and writes Position, Velocity and Forces; the
+ * colour fields are never touched (the UI recolours picked particles in place,
+ * SimulationState.cpp:364-396).
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NB_API __attribute__((visibility("default")))
+#else
+#define NB_API
+#endif
+
+typedef struct nb_sim* nb_handle;
+
+typedef enum nb_status
+{
+    NB_OK = 0,
+    NB_ERR_ARG = -1,      /* null / out-of-range argument, wrong stride, handle not initialised */
+    NB_ERR_CUDA = -2,     /* CUDA runtime error, no device, or no sm_100a kernel image */
+    NB_ERR_NCCL = -3,     /* NCCL missing or failed */
+    NB_ERR_STATE = -4,    /* call not valid in the handle's mode / before nb_init_* */
+    NB_ERR_NOMEM = -5
+} nb_status;
+
+/* Which reference sim the handle stands in for (ENBodySim, INBodySim.hpp:11-17). */
+typedef enum nb_mode
+{
+    NB_MODE_ALLPAIRS = 0,   /* BruteForceCPU / BruteForceGPU: exact O(N^2) sum          */
+    NB_MODE_BARNESHUT = 2   /* BarnesHut: per-step octree rebuild + theta-walk           */
+} nb_mode;
+
+#define NB_PARTICLE_STRIDE 104
+#define NB_OFF_POSITION 0
+#define NB_OFF_VELOCITY 48
+#define NB_OFF_FORCES 72
+#define NB_OFF_MASS 96
+
+typedef struct nb_config
+{
+    uint32_t struct_size;    /* = sizeof(nb_config); set by nb_default_config                      */
+    int32_t  device;         /* CUDA device ordinal                                                */
+    int32_t  mode;           /* nb_mode                                                            */
+    float    theta;          /* Octree::Theta (Octree.cpp:5 default 2.0; benchmarks use 0.5)       */
+    double   G;              /* Phys::G  = 6.674e-11   (Physics.hpp:9)                             */
+    double   softening;      /* Phys::S  = 10, ADDED to d^2 (Physics.hpp:10,34)                    */
+    double   position_scale; /* Phys::StarSystemScale = 2.3e13 (Physics.hpp:13,16)                 */
+    float    bounds;         /* half-width of the fixed octree root cube = 4000 (BarnesHut.cpp:14) */
+    int32_t  rank;           /* this handle integrates bodies [rank*N/world, (rank+1)*N/world)     */
+    int32_t  world;          /* number of cooperating handles (one per GPU); 1 = single GPU        */
+    void*    stream;         /* cudaStream_t to launch on; NULL = a private non-blocking stream    */
+    int32_t  source_splits;  /* all-pairs: source-range splits per target block, 0 = auto          */
+    int32_t  kernel_variant; /* all-pairs inner-loop variant, 0 = default          */
+} nb_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+NB_API int nb_abi_version(void);
+NB_API const char* nb_last_error(void);
+NB_API int nb_default_config(nb_config* cfg);
+/* CreateNBodySim(ctx, type) -- INBodySim.cpp:7-27 */
+NB_API int nb_create(const nb_config* cfg, nb_handle* out);
+NB_API int nb_destroy(nb_handle h);
+/* BHThetaChanged event -> Octree::Theta -- BarnesHut.cpp:29-31 */
+NB_API int nb_set_theta(nb_handle h, float theta);
+
+/* ---- INBodySim::Init ----------------------------------------------------------------------- */
+/* Init(std::vector<Particle>&) -- BruteForceCPU.cpp:20-23, BarnesHut.cpp:39-42.  `particles` is a
+ * HOST array of n records of `stride` bytes laid out as above (stride >= 104).  The data is
+ * copied to the device; the caller keeps ownership. */
+NB_API int nb_init_aos(nb_handle h, const void* particles, size_t n, size_t stride);
+/* Same from structure-of-arrays HOST buffers: pos[3n] float, vel[3n] double, mass[n] double. */
+NB_API int nb_init_soa(nb_handle h, const float* pos3, const double* vel3, const double* mass, size_t n);
+
+/* ---- IParticleSeeder::Seed ----------------------------------------------------------------- */
+/* GalaxySeeder<Particle>(particles, scale).Seed(seed) -- GalaxySeeder.cpp:43-80 -- into a HOST
+ * AoS buffer, bit-identical to the reference built with g++/libstdc++ (the random engine and
+ * distributions are implementation-defined).  Does not need a handle. */
+NB_API int nb_seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale);
+/* Two-galaxy collision scene used by config 5 (defined by this repo): galaxies seeded
+ * with `seed` and `seed+1`, n/2 bodies each, offset by -/+ `separation`/2 along x and approaching
+ * each other with `approach_speed` (velocity units). */
+NB_API int nb_seed_collision_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale,
+                           float separation, double approach_speed);
+/* Device-side galaxy seeder: counter-based generator, same distributions as GalaxySeeder.cpp but
+ * not the same random stream; initialises the handle directly (no host round trip). */
+NB_API int nb_seed_galaxy_device(nb_handle h, size_t n, uint64_t seed, float scale);
+
+/* ---- INBodySim::Update --------------------------------------------------------------------- */
+/* nsteps x Update(dt) on device-resident state -- BruteForceCPU.cpp:45-74 / BarnesHut.cpp:44-96:
+ * accelerations, then kick-drift  v += a*dt;  pos += (float)(v*dt/position_scale).
+ * Asynchronous on the handle's stream; with world > 1 it performs the per-step position exchange. */
+NB_API int nb_step(nb_handle h, float dt, int nsteps);
+/* Update(dt) with the reference's host-memory contract: upload Position/Velocity/Mass from the
+ * caller's AoS array, one step, write Position/Velocity/Forces back, synchronous on return
+ * (SimulationState.cpp:52-60 copies the array to a vertex buffer right after Update). */
+NB_API int nb_update_aos(nb_handle h, void* particles, size_t n, size_t stride, float dt);
+/* Wait for everything queued on the handle's stream. */
+NB_API int nb_sync(nb_handle h);
+
+/* ---- read back ------------------------------------------------------------------------------ */
+/* Writes Position, Velocity, Forces of all bodies this handle owns into the HOST AoS array
+ * (records [first, first+count) of nb_owned_range).  Forces follow the reference: zero in
+ * all-pairs mode (BruteForceCPU.cpp:72), mass * acceleration of the last step in Barnes-Hut
+ * mode (BarnesHut.cpp:75,108). */
+NB_API int nb_read_aos(nb_handle h, void* particles, size_t n, size_t stride);
+NB_API int nb_read_soa(nb_handle h, float* pos3, double* vel3);
+NB_API int nb_owned_range(nb_handle h, size_t* first, size_t* count);
+NB_API int nb_num_bodies(nb_handle h, size_t* n);
+
+/* ---- parity hooks --------------------------------------------------------------------------- */
+/* Accelerations (Forces / Mass of the reference) of the owned bodies for the CURRENT positions,
+ * without integrating: acc3[3*count] doubles. */
+NB_API int nb_compute_accel(nb_handle h);
+NB_API int nb_get_accel(nb_handle h, double* acc3);
+/* Barnes-Hut topology of the last build: number of in-bounds bodies, their 63-bit Morton codes in
+ * sorted order and the body index of each sorted slot (bodies outside the root cube are dropped
+ * as sources, Octree.cpp:58-62). */
+NB_API int nb_get_morton(nb_handle h, uint64_t* codes, uint32_t* order, size_t* n_inbounds);
+/* Radix-tree topology: for each of the n_inbounds-1 internal nodes the left/right child
+ * (>= 0: internal node index, < 0: ~sorted leaf slot), the common-prefix length in bits, the
+ * mass and centre of mass.  Any pointer may be NULL. */
+NB_API int nb_get_tree(nb_handle h, int32_t* left, int32_t* right, int32_t* prefix_bits, double* mass,
+                float* com3, size_t* n_internal);
+/* Counters of the last traversal summed over owned targets: {accepted cells, pair (leaf)
+ * evaluations, node visits}. */
+NB_API int nb_get_walk_stats(nb_handle h, uint64_t stats3[3]);
+/* Kinetic and potential energy of the conserved quantity of this force law,
+ * E = sum 1/2 m v^2 + position_scale * sum_{i<j} U(r), U = -(G ma mb / sqrt(S)) atan(sqrt(S)/r),
+ * potential by exact pair sum over owned targets x all sources (O(N^2/world)). */
+NB_API int nb_energy(nb_handle h, double* kinetic, double* potential);
+
+/* ---- multi-GPU plumbing ---------------------------------------------------------------------- */
+/* One handle per process/GPU.  The host (torch.distributed, MPI, ...) moves 128 opaque bytes from
+ * rank 0 to everyone; the library then owns an NCCL communicator and all-gathers the float4
+ * {x,y,z,G*m} of the owned bodies after every kick-drift. */
+NB_API int nb_comm_unique_id(uint8_t id[128]);
+NB_API int nb_comm_init(nb_handle h, const uint8_t id[128]);
+/* Raw device pointers for hosts that prefer to run the exchange themselves (e.g. through
+ * torch.distributed.all_gather_into_tensor): the float4 array of all n bodies. */
+NB_API int nb_device_posw(nb_handle h, void** dev_ptr, size_t* bytes);
+/* Tells the handle that the host exchanged positions itself after the last step. */
+NB_API int nb_mark_exchanged(nb_handle h);
+
+/* ---- measurement ----------------------------------------------------------------------------- */
+/* Device time in milliseconds (CUDA events on the handle's stream) of the last nb_step call and of
+ * its dominant kernel, and how many kernels that call launched. */
+NB_API int nb_last_step_timing(nb_handle h, float* total_ms, float* force_kernel_ms, int* launches);
+/* Pure-FFMA issue-rate probe: sustained FP32 FLOP/s of this device as measured now. */
+NB_API int nb_probe_fp32_peak(nb_handle h, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_B200_H */

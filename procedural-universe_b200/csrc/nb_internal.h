@@ -1,0 +1,132 @@
+// Internal state of one engine handle.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/nbody_b200.h"
+
+namespace nb
+{
+
+void set_error(const char* fmt, ...);
+
+#define NB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            nb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+            return NB_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define NB_CHECK(call)                                                                             \
+    do {                                                                                           \
+        int s_ = (call);                                                                           \
+        if (s_ != NB_OK) return s_;                                                                \
+    } while (0)
+
+#define NB_REQUIRE(cond, status, msg)                                                              \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            nb::set_error("%s: %s", __func__, msg);                                                \
+            return status;                                                                         \
+        }                                                                                          \
+    } while (0)
+
+// Barnes-Hut working set of one handle (tree.cu).
+struct TreeBuffers
+{
+    size_t capacity = 0;            // bodies the buffers were sized for
+    uint64_t* keys[2] = {nullptr, nullptr};   // Morton codes, ping-pong for the radix sort
+    uint32_t* vals[2] = {nullptr, nullptr};   // body index per slot, ping-pong
+    uint32_t* hist = nullptr;       // radix-sort block histograms
+    size_t hist_words = 0;
+    uint32_t* counters = nullptr;   // [0] in-bounds bodies, [1..] scratch
+    int32_t* child = nullptr;       // [2][n-1] left/right child of internal node (>=0 internal, <0 ~leaf)
+    int32_t* parent = nullptr;      // [2n-1]   parent of internal nodes then of leaves
+    int32_t* prefix = nullptr;      // [n-1]    common-prefix length in bits (0..63; 64+ = duplicate codes)
+    int32_t* range = nullptr;       // [2][n-1] first/last sorted slot covered
+    uint32_t* flags = nullptr;      // [n-1]    arrival counters of the bottom-up pass
+    double* nmass = nullptr;        // [2n-1]   mass  (internal nodes, then leaves)
+    double* ncom = nullptr;         // [3][2n-1] mass-weighted position sums -> centre of mass
+    float4* walk_a = nullptr;       // [2n-1] {com.x, com.y, com.z, G*M}
+    int4* walk_b = nullptr;         // [2n-1] {open threshold (float bits), first slot, next-if-open, next-if-skip}
+    unsigned long long* stats = nullptr;   // [3] accepted cells, pair evals, node visits
+    int sort_bits_done = 0;
+    int cur = 0;                    // which ping-pong half holds the sorted result
+    size_t n_inbounds_host = 0;
+    bool built = false;
+};
+
+}  // namespace nb
+
+struct nb_sim
+{
+    nb_config cfg;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    size_t n = 0;          // all bodies (sources)
+    size_t first = 0;      // owned (target) range
+    size_t count = 0;
+
+    float4* posw = nullptr;      // [n]        {x, y, z, (float)(G*m)}
+    double* vel = nullptr;       // [3][count] velocity planes of owned bodies
+    double* mass = nullptr;      // [count]
+    double* acc = nullptr;       // [3][count] accelerations of the last force evaluation
+    double* acc_part = nullptr;  // [splits][3][count] all-pairs partial sums
+    size_t acc_part_splits = 0;
+
+    void* d_aos = nullptr;       // device image of the caller's AoS array
+    size_t d_aos_bytes = 0;
+
+    int ap_kernel = 0;           // index into allpairs_table()
+    int ap_splits = 1;
+    bool acc_valid = false;
+    bool forces_from_last_step = false;
+    bool exchanged = true;       // posw of remote ranks is current
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // step begin/end, force kernel begin/end
+    bool timing_valid = false;
+    int last_launches = 0;
+    unsigned long long total_launches = 0;
+
+    nb::TreeBuffers tree;
+
+    void* nccl_comm = nullptr;   // ncclComm_t
+};
+
+namespace nb
+{
+// allpairs / integrator (nb_api.cu, integrate.cu)
+int launch_allpairs(nb_sim* h);
+int launch_kick_drift(nb_sim* h, float dt);
+int launch_unpack_aos(nb_sim* h, size_t stride);
+int launch_pack_aos(nb_sim* h, size_t stride, bool forces_zero);
+int choose_allpairs_config(nb_sim* h);
+
+// tree.cu
+int tree_reserve(nb_sim* h);
+void tree_release(nb_sim* h);
+int tree_build(nb_sim* h);
+int tree_walk(nb_sim* h);
+
+// nccl_dl.cpp
+int comm_unique_id(uint8_t id[128]);
+int comm_init(nb_sim* h, const uint8_t id[128]);
+int comm_allgather_posw(nb_sim* h);
+void comm_destroy(nb_sim* h);
+
+// seed_host.cpp / seed_device.cu
+int seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale);
+int seed_galaxy_device(nb_sim* h, size_t n, uint64_t seed, float scale);
+
+// energy.cu
+int energy(nb_sim* h, double* ke, double* pe);
+
+// probe.cu
+int probe_fp32_peak(nb_sim* h, double* flops);
+}  // namespace nb
