@@ -45,7 +45,7 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 template <int THREADS, int T, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_allpairs_scalar(const float4* __restrict__ posw, int n, int tgt_first, int tgt_count, int src_chunk,
-                  double* __restrict__ out, float sc)
+                  double* __restrict__ out, float sc, float soft, const float* __restrict__ wmax)
 {
     constexpr int TILE = 2 * THREADS;
     __shared__ float4 sm[2][TILE];
@@ -153,7 +153,7 @@ k_allpairs_scalar(const float4* __restrict__ posw, int n, int tgt_first, int tgt
 template <int THREADS, int T, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_allpairs_srcpair(const float4* __restrict__ posw, int n, int tgt_first, int tgt_count, int src_chunk,
-                   double* __restrict__ out, float sc)
+                   double* __restrict__ out, float sc, float soft, const float* __restrict__ wmax)
 {
     constexpr int TILE = 2 * THREADS;      // sources per tile
     constexpr int PAIRS = THREADS;         // source pairs per tile
@@ -269,7 +269,7 @@ k_allpairs_srcpair(const float4* __restrict__ posw, int n, int tgt_first, int tg
 template <int THREADS, int T, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_allpairs_tgtpair(const float4* __restrict__ posw, int n, int tgt_first, int tgt_count, int src_chunk,
-                   double* __restrict__ out, float sc)
+                   double* __restrict__ out, float sc, float soft, const float* __restrict__ wmax)
 {
     static_assert(T % 2 == 0, "targets are processed in pairs");
     constexpr int TP = T / 2;
@@ -382,25 +382,298 @@ k_allpairs_tgtpair(const float4* __restrict__ posw, int n, int tgt_first, int tg
 }
 
 // ------------------------------------------------------------------------------------------------
+// Variant 3: variant 1 with the source weight folded under the rsqrt -- 12 FMA-pipe ops + 1 MUFU.
+//
+//     w / (|d| (d^2+S)) = rsqrt( d^2 * (a (d^2+S))^2 ),   a = 1 / w
+//
+// so the multiply by w disappears if the tile holds a and b = S a per source:
+//     t = fma(d2, a, b);  u = d2 * t;  x = fma(u, t, eps);  s = rsqrt(x);  acc += s * d.
+// To stay inside fp32 the weights are normalised by W = 2^ceil(log2(max_j w_j)) (exact scaling,
+// undone exactly in the epilogue) and a carries the same 2^-27 pre-scale as the other variants:
+// a = 2^-27 W / w >= 2^-27.  Light bodies have a large `a`; their term overflows to rsqrt(inf) = 0
+// only where it is < 1e-20 of a unit-weight body's at the same distance.  Massless bodies
+// (a = inf) are clamped to a = 1e18 so that their own self term stays finite (0 * finite).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2_ceil(float m)
+{
+    // smallest power of two >= m for normal m > 0 (exact powers of two map to themselves * 2; harmless)
+    return __int_as_float((__float_as_int(m) & 0x7f800000) + 0x00800000);
+}
+
+template <int THREADS, int T, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_allpairs_fold(const float4* __restrict__ posw, int n, int tgt_first, int tgt_count, int src_chunk,
+                double* __restrict__ out, float sc, float soft, const float* __restrict__ wmax)
+{
+    constexpr int TILE = 2 * THREADS;
+    constexpr int PAIRS = THREADS;
+    __shared__ float4 smA[2][PAIRS];   // {x0,x1,y0,y1}
+    __shared__ float4 smB[2][PAIRS];   // {z0,z1,a0,a1}
+    __shared__ float2 smC[2][PAIRS];   // {b0,b1}
+
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.y * src_chunk;
+    const int j1 = min(n, j0 + src_chunk);
+    const int base = blockIdx.x * (THREADS * T) + tid;
+    const float W = pow2_ceil(fmaxf(*wmax, 1.17549435e-38f));
+    const float cW = kPreScale * W;
+
+    float2 npx[T], npy[T], npz[T];
+    double dax[T], day[T], daz[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+    {
+        const int li = base + t * THREADS;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (li < tgt_count) p = posw[tgt_first + li];
+        npx[t] = make_float2(-p.x, -p.x);
+        npy[t] = make_float2(-p.y, -p.y);
+        npz[t] = make_float2(-p.z, -p.z);
+        dax[t] = day[t] = daz[t] = 0.0;
+    }
+    const float2 eps2 = make_float2(kEps, kEps);
+
+    const int ntiles = (j1 - j0 + TILE - 1) / TILE;
+    float4 preA, preB;
+    float2 preC;
+    auto fetch = [&](int tile) {
+        const int j = j0 + tile * TILE + 2 * tid;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        if (j < j1) s0 = posw[j];
+        if (j + 1 < j1) s1 = posw[j + 1];
+        const float a0 = fminf(__fdiv_rn(cW, s0.w), 1e18f);   // w = 0 (padding, massless) -> clamp
+        const float a1 = fminf(__fdiv_rn(cW, s1.w), 1e18f);
+        preA = make_float4(s0.x, s1.x, s0.y, s1.y);
+        preB = make_float4(s0.z, s1.z, a0, a1);
+        preC = make_float2(soft * a0, soft * a1);
+    };
+    auto stash = [&](int buf) {
+        smA[buf][tid] = preA;
+        smB[buf][tid] = preB;
+        smC[buf][tid] = preC;
+    };
+
+    if (ntiles > 0) { fetch(0); stash(0); }
+    __syncthreads();
+
+    for (int tile = 0; tile < ntiles; ++tile)
+    {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) fetch(tile + 1);
+
+        float2 ax[T], ay[T], az[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
+
+#pragma unroll 4
+        for (int jp = 0; jp < PAIRS; ++jp)
+        {
+            const float4 A = smA[buf][jp];
+            const float4 B = smB[buf][jp];
+            const float2 sb = smC[buf][jp];
+            const float2 sx = make_float2(A.x, A.y), sy = make_float2(A.z, A.w);
+            const float2 sz = make_float2(B.x, B.y), sa = make_float2(B.z, B.w);
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+            {
+                const float2 dx = __fadd2_rn(sx, npx[t]);
+                const float2 dy = __fadd2_rn(sy, npy[t]);
+                const float2 dz = __fadd2_rn(sz, npz[t]);
+                float2 d2 = __fmul2_rn(dx, dx);
+                d2 = __ffma2_rn(dy, dy, d2);
+                d2 = __ffma2_rn(dz, dz, d2);
+                const float2 tt = __ffma2_rn(d2, sa, sb);
+                const float2 u = __fmul2_rn(d2, tt);
+                const float2 x = __ffma2_rn(u, tt, eps2);
+                const float2 s = make_float2(rsqrt_approx(x.x), rsqrt_approx(x.y));
+                ax[t] = __ffma2_rn(s, dx, ax[t]);
+                ay[t] = __ffma2_rn(s, dy, ay[t]);
+                az[t] = __ffma2_rn(s, dz, az[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+        {
+            dax[t] += (double)(ax[t].x + ax[t].y);
+            day[t] += (double)(ay[t].x + ay[t].y);
+            daz[t] += (double)(az[t].x + az[t].y);
+        }
+        if (tile + 1 < ntiles) stash(buf ^ 1);
+        __syncthreads();
+    }
+
+    double* o = out + (size_t)blockIdx.y * 3 * (size_t)tgt_count;
+    const double Wd = (double)W * (double)kPreScale;   // rsqrt(x) = (w/W) 2^27 / (|d| (d^2+S))
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+    {
+        const int li = base + t * THREADS;
+        if (li < tgt_count)
+        {
+            o[li] = dax[t] * Wd;
+            o[(size_t)tgt_count + li] = day[t] * Wd;
+            o[2 * (size_t)tgt_count + li] = daz[t] * Wd;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Variant 4: variant 3 tuned for the issue port.  ncu on variants 1/3 shows the FMA pipe ~85 %
+// busy with `math pipe throttle` the only stall: on sm_100 every packed f32x2 op and every MUFU
+// holds the issue port for 2 cycles and every other instruction for 1, so the floor per
+// interaction is 12 (FMA) + 2 (MUFU) + whatever else the loop issues.  This variant trims the
+// "whatever else": the fp64 running sums live in shared memory (touched once per 512-source tile)
+// instead of 6 T registers, which lets a thread own more targets (fewer LDS per interaction)
+// inside the 128-register budget, and b = S a of two source pairs shares one LDS.128.
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int T, int MINB, int UNROLL>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_allpairs_fold2(const float4* __restrict__ posw, int n, int tgt_first, int tgt_count, int src_chunk,
+                 double* __restrict__ out, float sc, float soft, const float* __restrict__ wmax)
+{
+    constexpr int TILE = 2 * THREADS;
+    constexpr int PAIRS = THREADS;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float4 (*smA)[PAIRS] = reinterpret_cast<float4 (*)[PAIRS]>(dyn_smem);                        // {x0,x1,y0,y1}
+    float4 (*smB)[PAIRS] = reinterpret_cast<float4 (*)[PAIRS]>(dyn_smem + 2 * PAIRS * 16);       // {z0,z1,a0,a1}
+    float4 (*smC)[PAIRS / 2] = reinterpret_cast<float4 (*)[PAIRS / 2]>(dyn_smem + 4 * PAIRS * 16);   // {b of pair 2k, b of pair 2k+1}
+    double (*sacc)[THREADS] = reinterpret_cast<double (*)[THREADS]>(dyn_smem + 5 * PAIRS * 16);  // [3T][THREADS]
+
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.y * src_chunk;
+    const int j1 = min(n, j0 + src_chunk);
+    const int base = blockIdx.x * (THREADS * T) + tid;
+    const float W = pow2_ceil(fmaxf(*wmax, 1.17549435e-38f));
+    const float cW = kPreScale * W;
+
+    float2 npx[T], npy[T], npz[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+    {
+        const int li = base + t * THREADS;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (li < tgt_count) p = posw[tgt_first + li];
+        npx[t] = make_float2(-p.x, -p.x);
+        npy[t] = make_float2(-p.y, -p.y);
+        npz[t] = make_float2(-p.z, -p.z);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sacc[3 * t + c][tid] = 0.0;
+    }
+    const float2 eps2 = make_float2(kEps, kEps);
+
+    const int ntiles = (j1 - j0 + TILE - 1) / TILE;
+    float4 preA, preB;
+    float2 preC;
+    auto fetch = [&](int tile) {
+        const int j = j0 + tile * TILE + 2 * tid;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        if (j < j1) s0 = posw[j];
+        if (j + 1 < j1) s1 = posw[j + 1];
+        const float a0 = fminf(__fdiv_rn(cW, s0.w), 1e18f);
+        const float a1 = fminf(__fdiv_rn(cW, s1.w), 1e18f);
+        preA = make_float4(s0.x, s1.x, s0.y, s1.y);
+        preB = make_float4(s0.z, s1.z, a0, a1);
+        preC = make_float2(soft * a0, soft * a1);
+    };
+    auto stash = [&](int buf) {
+        smA[buf][tid] = preA;
+        smB[buf][tid] = preB;
+        reinterpret_cast<float2*>(&smC[buf][0])[tid] = preC;
+    };
+
+    if (ntiles > 0) { fetch(0); stash(0); }
+    __syncthreads();
+
+    for (int tile = 0; tile < ntiles; ++tile)
+    {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) fetch(tile + 1);
+
+        float2 ax[T], ay[T], az[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) ax[t] = ay[t] = az[t] = make_float2(0.f, 0.f);
+
+#pragma unroll UNROLL
+        for (int jq = 0; jq < PAIRS / 2; ++jq)
+        {
+            const float4 C = smC[buf][jq];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                const float4 A = smA[buf][2 * jq + h];
+                const float4 B = smB[buf][2 * jq + h];
+                const float2 sx = make_float2(A.x, A.y), sy = make_float2(A.z, A.w);
+                const float2 sz = make_float2(B.x, B.y), sa = make_float2(B.z, B.w);
+                const float2 sb = h == 0 ? make_float2(C.x, C.y) : make_float2(C.z, C.w);
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                {
+                    const float2 dx = __fadd2_rn(sx, npx[t]);
+                    const float2 dy = __fadd2_rn(sy, npy[t]);
+                    const float2 dz = __fadd2_rn(sz, npz[t]);
+                    float2 d2 = __fmul2_rn(dx, dx);
+                    d2 = __ffma2_rn(dy, dy, d2);
+                    d2 = __ffma2_rn(dz, dz, d2);
+                    const float2 tt = __ffma2_rn(d2, sa, sb);
+                    const float2 u = __fmul2_rn(d2, tt);
+                    const float2 x = __ffma2_rn(u, tt, eps2);
+                    const float2 s = make_float2(rsqrt_approx(x.x), rsqrt_approx(x.y));
+                    ax[t] = __ffma2_rn(s, dx, ax[t]);
+                    ay[t] = __ffma2_rn(s, dy, ay[t]);
+                    az[t] = __ffma2_rn(s, dz, az[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+        {
+            sacc[3 * t + 0][tid] += (double)(ax[t].x + ax[t].y);
+            sacc[3 * t + 1][tid] += (double)(ay[t].x + ay[t].y);
+            sacc[3 * t + 2][tid] += (double)(az[t].x + az[t].y);
+        }
+        if (tile + 1 < ntiles) stash(buf ^ 1);
+        __syncthreads();
+    }
+
+    double* o = out + (size_t)blockIdx.y * 3 * (size_t)tgt_count;
+    const double Wd = (double)W * (double)kPreScale;
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+    {
+        const int li = base + t * THREADS;
+        if (li < tgt_count)
+        {
+            o[li] = sacc[3 * t + 0][tid] * Wd;
+            o[(size_t)tgt_count + li] = sacc[3 * t + 1][tid] * Wd;
+            o[2 * (size_t)tgt_count + li] = sacc[3 * t + 2][tid] * Wd;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Launch table shared by the library and the tuner.
 // ------------------------------------------------------------------------------------------------
 struct AllPairsKernel
 {
     const char* name;
-    int variant;       // 0 scalar, 1 source pairs, 2 target pairs
+    int variant;       // 0 scalar, 1 source pairs, 2 target pairs, 3 source pairs with folded weight
     int threads;
     int targets;       // targets per thread
     int min_blocks;    // __launch_bounds__ min blocks per SM
-    void (*fn)(const float4*, int, int, int, int, double*, float);
+    int smem_bytes;    // dynamic shared memory per CTA (0: the kernel only uses static shared memory)
+    void (*fn)(const float4*, int, int, int, int, double*, float, float, const float*);
 };
 
 #define NB_AP_ENTRY(KERNEL, VAR, TH, T, MB) \
-    { #KERNEL "<" #TH "," #T "," #MB ">", VAR, TH, T, MB, KERNEL<TH, T, MB> }
+    { #KERNEL "<" #TH "," #T "," #MB ">", VAR, TH, T, MB, 0, KERNEL<TH, T, MB> }
+#define NB_AP_ENTRY4(TH, T, MB, UN) \
+    { "k_allpairs_fold2<" #TH "," #T "," #MB "," #UN ">", 3, TH, T, MB, 5 * TH * 16 + 3 * T * TH * 8, k_allpairs_fold2<TH, T, MB, UN> }
 
 inline const AllPairsKernel* allpairs_table(int* count)
 {
     static const AllPairsKernel table[] = {
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 4, 2),   // index 0 = library default
+        NB_AP_ENTRY4(256, 4, 2, 2),                      // index 0 = library default (fastest at 1e-5 parity)
+        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 4, 2),
         NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 2, 2),
         NB_AP_ENTRY(k_allpairs_srcpair, 1, 128, 4, 4),
         NB_AP_ENTRY(k_allpairs_srcpair, 1, 128, 2, 4),
@@ -418,6 +691,25 @@ inline const AllPairsKernel* allpairs_table(int* count)
         NB_AP_ENTRY(k_allpairs_scalar, 0, 256, 2, 3),
         NB_AP_ENTRY(k_allpairs_scalar, 0, 128, 4, 4),
         NB_AP_ENTRY(k_allpairs_scalar, 0, 256, 8, 2),
+        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 2, 2),      // 18
+        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 4, 2),
+        NB_AP_ENTRY(k_allpairs_fold, 3, 128, 2, 4),
+        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 2, 3),
+        NB_AP_ENTRY(k_allpairs_fold, 3, 512, 2, 1),
+        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 1, 4),
+        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 1, 4),
+        NB_AP_ENTRY4(256, 2, 2, 2),                      // 25
+        NB_AP_ENTRY4(256, 4, 2, 1),
+        NB_AP_ENTRY4(256, 4, 2, 2),
+        NB_AP_ENTRY4(256, 3, 2, 2),
+        NB_AP_ENTRY4(128, 4, 4, 1),
+        NB_AP_ENTRY4(128, 4, 4, 2),                      // 30
+        NB_AP_ENTRY4(256, 6, 1, 1),
+        NB_AP_ENTRY4(256, 8, 1, 1),
+        NB_AP_ENTRY4(512, 4, 1, 1),
+        NB_AP_ENTRY4(256, 2, 3, 2),
+        NB_AP_ENTRY4(384, 4, 1, 1),                      // 35
+        NB_AP_ENTRY4(128, 6, 3, 1),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

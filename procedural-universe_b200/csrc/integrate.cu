@@ -62,14 +62,21 @@ k_reduce_partials(const double* __restrict__ acc_part, int splits, int count, do
 // AoS -> SoA.  Every body's position and G*m go to posw (all ranks need all sources); velocity and
 // mass only for the owned range.
 __global__ void __launch_bounds__(256)
-k_unpack_aos(const unsigned char* __restrict__ aos, size_t stride, int n, int first, int count,
-             float4* __restrict__ posw, double* __restrict__ vel, double* __restrict__ mass, double G)
+k_unpack_aos(const unsigned char* __restrict__ aos, size_t stride, int begin, int end, int first, int count,
+             float4* __restrict__ posw, double* __restrict__ vel, double* __restrict__ mass, double G,
+             int* __restrict__ wmax_bits)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned char* rec = aos + (size_t)i * stride;
-    const float* pos = reinterpret_cast<const float*>(rec + NB_OFF_POSITION);
+    const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < end;
+    float w = 0.f;
+    const unsigned char* rec = aos + (size_t)(live ? i : begin) * stride;
     const double m = *reinterpret_cast<const double*>(rec + NB_OFF_MASS);
+    if (live) w = fmaxf((float)(G * m), 0.f);
+    // max_j w_j for the weight-folded all-pairs kernel: non-negative floats order like their bits
+    const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(w));
+    if ((threadIdx.x & 31) == 0) atomicMax(wmax_bits, wmax);
+    if (!live) return;
+    const float* pos = reinterpret_cast<const float*>(rec + NB_OFF_POSITION);
     posw[i] = make_float4(pos[0], pos[1], pos[2], (float)(G * m));
     const int li = i - first;
     if (li >= 0 && li < count)
@@ -134,11 +141,12 @@ int launch_reduce_partials(nb_sim* h)
     return NB_OK;
 }
 
-int launch_unpack_aos(nb_sim* h, size_t stride)
+int launch_unpack_aos(nb_sim* h, size_t stride, size_t begin, size_t end)
 {
-    k_unpack_aos<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(
-        static_cast<const unsigned char*>(h->d_aos), stride, (int)h->n, (int)h->first, (int)h->count,
-        h->posw, h->vel, h->mass, h->cfg.G);
+    if (begin == 0 && end == h->n) NB_CUDA(cudaMemsetAsync(h->wmax, 0, sizeof(float), h->stream));
+    k_unpack_aos<<<blocks_for(end - begin, 256), 256, 0, h->stream>>>(
+        static_cast<const unsigned char*>(h->d_aos), stride, (int)begin, (int)end, (int)h->first, (int)h->count,
+        h->posw, h->vel, h->mass, h->cfg.G, reinterpret_cast<int*>(h->wmax));
     NB_CUDA(cudaGetLastError());
     ++h->last_launches;
     return NB_OK;

@@ -20,8 +20,6 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
-int launch_reduce_partials(nb_sim* h);
-
 static int free_state(nb_sim* h)
 {
     cudaFree(h->posw); h->posw = nullptr;
@@ -60,7 +58,8 @@ int choose_allpairs_config(nb_sim* h)
     const AllPairsKernel& k = table[idx];
 
     int occ = 0;
-    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k.fn, k.threads, 0));
+    if (k.smem_bytes > 0) NB_CUDA(cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
+    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k.fn, k.threads, k.smem_bytes));
     if (occ < 1) occ = 1;
     const long slots = (long)occ * h->sm_count;
     const long tgt_blocks = ((long)h->count + (long)k.threads * k.targets - 1) / ((long)k.threads * k.targets);
@@ -111,8 +110,8 @@ int launch_allpairs(nb_sim* h)
     const long tgt_blocks = ((long)h->count + (long)k.threads * k.targets - 1) / ((long)k.threads * k.targets);
     dim3 grid((unsigned)tgt_blocks, (unsigned)splits, 1);
     const float sc = (float)(h->cfg.softening * (double)kPreScale);
-    k.fn<<<grid, k.threads, 0, h->stream>>>(h->posw, (int)h->n, (int)h->first, (int)h->count, (int)chunk,
-                                           h->acc_part, sc);
+    k.fn<<<grid, k.threads, k.smem_bytes, h->stream>>>(h->posw, (int)h->n, (int)h->first, (int)h->count, (int)chunk,
+                                           h->acc_part, sc, (float)h->cfg.softening, h->wmax);
     NB_CUDA(cudaGetLastError());
     ++h->last_launches;
     return NB_OK;
@@ -226,6 +225,11 @@ int nb_create(const nb_config* cfg, nb_handle* out)
         if (e != cudaSuccess) { delete h; nb::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
         h->own_stream = true;
     }
+    {
+        cudaError_t e = cudaMalloc(&h->wmax, sizeof(float));
+        if (e == cudaSuccess) e = cudaMemset(h->wmax, 0, sizeof(float));
+        if (e != cudaSuccess) { nb::set_error("cudaMalloc: %s", cudaGetErrorString(e)); nb_destroy(h); return NB_ERR_CUDA; }
+    }
     for (int i = 0; i < 4; ++i)
     {
         cudaError_t e = cudaEventCreate(&h->ev[i]);
@@ -243,6 +247,7 @@ int nb_destroy(nb_handle h)
     comm_destroy(h);
     free_state(h);
     cudaFree(h->d_aos);
+    cudaFree(h->wmax);
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -268,7 +273,7 @@ int nb_init_aos(nb_handle h, const void* particles, size_t n, size_t stride)
     NB_CHECK(reserve_aos(h, n * stride));
     NB_CUDA(cudaMemcpyAsync(h->d_aos, particles, n * stride, cudaMemcpyHostToDevice, h->stream));
     h->last_launches = 0;
-    NB_CHECK(launch_unpack_aos(h, stride));
+    NB_CHECK(launch_unpack_aos(h, stride, 0, n));
     NB_CUDA(cudaStreamSynchronize(h->stream));
     return NB_OK;
 }
@@ -297,7 +302,7 @@ int nb_init_soa(nb_handle h, const float* pos3, const double* vel3, const double
         cudaError_t e = cudaMemcpyAsync(h->d_aos, tmp, n * stride, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) { nb::set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); rc = NB_ERR_CUDA; }
     }
-    if (rc == NB_OK) { h->last_launches = 0; rc = launch_unpack_aos(h, stride); }
+    if (rc == NB_OK) { h->last_launches = 0; rc = launch_unpack_aos(h, stride, 0, n); }
     cudaStreamSynchronize(h->stream);
     cudaFreeHost(tmp);
     return rc;
@@ -340,12 +345,21 @@ int nb_update_aos(nb_handle h, void* particles, size_t n, size_t stride, float d
     NB_REQUIRE(h != nullptr && particles != nullptr, NB_ERR_ARG, "null argument");
     NB_REQUIRE(stride >= NB_PARTICLE_STRIDE && stride % 8 == 0, NB_ERR_ARG, "stride must be >= 104 and a multiple of 8");
     NB_CUDA(cudaSetDevice(h->cfg.device));
-    if (n != h->n) NB_CHECK(set_bodies(h, n));
+    // A single handle re-reads the whole array (the caller may have edited any record).  A shard
+    // handle (world > 1) owns records [first, first+count) of the caller's array: it re-reads those
+    // and keeps the other ranks' positions from the last exchange.
+    const bool fresh = (n != h->n);
+    if (fresh) NB_CHECK(set_bodies(h, n));
     NB_CHECK(reserve_aos(h, n * stride));
-    NB_CUDA(cudaMemcpyAsync(h->d_aos, particles, n * stride, cudaMemcpyHostToDevice, h->stream));
+    const bool whole = fresh || h->cfg.world == 1;
+    const size_t begin = whole ? 0 : h->first, end = whole ? n : h->first + h->count;
+    NB_REQUIRE(whole || h->exchanged, NB_ERR_STATE, "positions of remote ranks are stale");
+    unsigned char* host_in = static_cast<unsigned char*>(particles);
+    NB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(h->d_aos) + begin * stride, host_in + begin * stride,
+                            (end - begin) * stride, cudaMemcpyHostToDevice, h->stream));
     h->last_launches = 0;
-    NB_CHECK(launch_unpack_aos(h, stride));
-    h->exchanged = true;
+    NB_CHECK(launch_unpack_aos(h, stride, begin, end));
+    if (whole) h->exchanged = true;
     const int unpack_launches = h->last_launches;
     NB_CHECK(nb_step(h, dt, 1));
     NB_CHECK(launch_pack_aos(h, stride, h->cfg.mode == NB_MODE_ALLPAIRS));

@@ -80,6 +80,7 @@ struct nb_sim
     double* acc_part = nullptr;  // [splits][3][count] all-pairs partial sums
     size_t acc_part_splits = 0;
 
+    float* wmax = nullptr;       // [1] max_j G*m_j over all sources (bit pattern, kept by atomicMax)
     void* d_aos = nullptr;       // device image of the caller's AoS array
     size_t d_aos_bytes = 0;
 
@@ -104,7 +105,8 @@ namespace nb
 // allpairs / integrator (nb_api.cu, integrate.cu)
 int launch_allpairs(nb_sim* h);
 int launch_kick_drift(nb_sim* h, float dt);
-int launch_unpack_aos(nb_sim* h, size_t stride);
+int launch_unpack_aos(nb_sim* h, size_t stride, size_t begin, size_t end);
+int launch_reduce_partials(nb_sim* h);
 int launch_pack_aos(nb_sim* h, size_t stride, bool forces_zero);
 int choose_allpairs_config(nb_sim* h);
 

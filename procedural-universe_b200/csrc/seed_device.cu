@@ -68,10 +68,13 @@ struct Counter
 };
 
 __global__ void __launch_bounds__(256)
-k_seed_galaxy(SeedParams P, float4* __restrict__ posw, double* __restrict__ vel, double* __restrict__ mass)
+k_seed_galaxy(SeedParams P, float4* __restrict__ posw, double* __restrict__ vel, double* __restrict__ mass,
+              int* __restrict__ wmax_bits)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    // heaviest possible body: G * 1e30 (every rank seeds all bodies, so a constant is exact enough)
+    if (i == 0) atomicMax(wmax_bits, __float_as_int((float)(P.G * 1e30)));
     Counter rng(P.seed, (unsigned int)i);
     float px, py, pz;
     double vx, vy, vz, m;
@@ -181,7 +184,7 @@ int seed_galaxy_device(nb_sim* h, size_t n, uint64_t seed, float scale)
     if (P.per_segment < 1) { P.per_segment = 1; P.arm_bodies = 0; }
     if ((size_t)P.arm_bodies > n) P.arm_bodies = (int)n;
     P.G = h->cfg.G;
-    k_seed_galaxy<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(P, h->posw, h->vel, h->mass);
+    k_seed_galaxy<<<(int)((n + 255) / 256), 256, 0, h->stream>>>(P, h->posw, h->vel, h->mass, reinterpret_cast<int*>(h->wmax));
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaStreamSynchronize(h->stream));
     return NB_OK;

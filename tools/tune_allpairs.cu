@@ -101,6 +101,10 @@ int main(int argc, char** argv)
     }
     float4* dp; CK(cudaMalloc(&dp, n * sizeof(float4)));
     CK(cudaMemcpy(dp, hp.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    float hwmax = 0.f;
+    for (int i = 0; i < n; ++i) hwmax = std::max(hwmax, hp[i].w);
+    float* dwmax; CK(cudaMalloc(&dwmax, sizeof(float)));
+    CK(cudaMemcpy(dwmax, &hwmax, sizeof(float), cudaMemcpyHostToDevice));
     const int max_splits = 16;
     double* dout; CK(cudaMalloc(&dout, (size_t)max_splits * 3 * n * sizeof(double)));
     std::vector<double> ref(3 * (size_t)n), cur((size_t)max_splits * 3 * n);
@@ -113,7 +117,8 @@ int main(int argc, char** argv)
     {
         const nb::AllPairsKernel& K = table[k];
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)K.fn, K.threads, 0));
+        if (K.smem_bytes > 0) CK(cudaFuncSetAttribute((const void*)K.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, K.smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)K.fn, K.threads, K.smem_bytes));
         const long slots = (long)occ * prop.multiProcessorCount;
         const long tb = ((long)n + K.threads * K.targets - 1) / (K.threads * K.targets);
         const int tile = K.variant == 2 ? K.threads : 2 * K.threads;
@@ -130,7 +135,7 @@ int main(int argc, char** argv)
         for (int r = 0; r < reps + 1; ++r)
         {
             CK(cudaEventRecord(e0));
-            K.fn<<<grid, K.threads>>>(dp, n, 0, n, (int)chunk, dout, sc);
+            K.fn<<<grid, K.threads, K.smem_bytes>>>(dp, n, 0, n, (int)chunk, dout, sc, 10.0f, dwmax);
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
             CK(cudaGetLastError());
             float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
