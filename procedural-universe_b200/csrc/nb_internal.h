@@ -39,8 +39,8 @@ void set_error(const char* fmt, ...);
 struct TreeBuffers
 {
     size_t capacity = 0;            // bodies the buffers were sized for
-    uint64_t* keys[2] = {nullptr, nullptr};   // Morton codes, ping-pong for the radix sort
-    uint32_t* vals[2] = {nullptr, nullptr};   // body index per slot, ping-pong
+    unsigned long long* keys[2] = {nullptr, nullptr};   // Morton codes, ping-pong for the radix sort
+    unsigned int* vals[2] = {nullptr, nullptr};         // body index per slot, ping-pong
     uint32_t* hist = nullptr;       // radix-sort block histograms
     size_t hist_words = 0;
     uint32_t* counters = nullptr;   // [0] in-bounds bodies, [1..] scratch

@@ -1,14 +1,759 @@
-// placeholder until the Barnes-Hut pipeline lands
+// Barnes-Hut on the GPU: K3 Morton encode, K4 radix sort, K5 Karras radix tree, K6 bottom-up
+// mass / centre-of-mass reduction, K7 warp-cooperative stackless traversal.
+//
+// What is being replaced: BarnesHut::Update (reference src/Sim/BarnesHut.cpp:44-96) rebuilds a
+// pointer octree every step (Octree::Add, Octree.cpp:53-84, eager 8-way Split :16-51), runs
+// Octree::CalculateMass (:86-105) and then Octree::CalculateForce (:107-145) per particle.
+// The reference's octree semantics that this file reproduces:
+//   * fixed root cube [-bounds, bounds)^3, half-open cells, child index z*4 + y*2 + x;
+//   * a cell with >= 2 bodies is internal, a single body sits in a leaf, empty children contribute
+//     nothing, bodies outside the root are dropped as sources but still receive forces;
+//   * acceptance  width / r < theta  tested top-down at EVERY internal cell (also cells that
+//     contain the target), leaves are always evaluated directly, the target itself is skipped.
+// How: bodies are sorted by the 63-bit Morton code of their level-21 cell; the Karras binary radix
+// tree over the sorted codes contains every internal octree cell as the node whose common prefix
+// first reaches that cell's level.  A radix-tree node with prefix delta lies in the octree cell of
+// level L = floor((delta-1)/3) (the 64-bit key has one leading zero); it OWNS octree cells iff
+// L > L(parent).  Owned chains of single-child cells share mass and centre of mass and their widths
+// shrink with depth, so "some cell of the chain is accepted" == "the deepest one is":
+// accept iff (width_L / theta)^2 < r^2.  Nodes that own no cell are never visited: the traversal
+// pointers (next-if-opened / next-if-skipped) jump over them.
+//
+// Determinism: the sort is a stable LSD radix sort, the tree is a pure function of the sorted
+// keys, and the bottom-up pass adds (left + right) in fp64 -- no order-dependent atomics -- so
+// every rank that holds the same positions builds bit-identical trees.
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
 #include "nb_internal.h"
+#include "allpairs.cuh"   // kPreScale, kEps, rsqrt_approx
+
 namespace nb
 {
-int tree_reserve(nb_sim*) { set_error("Barnes-Hut mode is not built yet"); return NB_ERR_STATE; }
-void tree_release(nb_sim*) {}
-int tree_build(nb_sim*) { set_error("Barnes-Hut mode is not built yet"); return NB_ERR_STATE; }
-int tree_walk(nb_sim*) { set_error("Barnes-Hut mode is not built yet"); return NB_ERR_STATE; }
+
+constexpr int kLevels = 21;
+constexpr unsigned long long kOutside = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kEnd = -1;
+constexpr int kNone = -2;
+
+// counters[] slots
+enum { C_INBOUNDS = 0, C_START = 1, C_WORDS = 8 };
+
+// ------------------------------------------------------------------------------------------------
+// K3: Morton codes.  Same comparison descent as the CPU restatement (oracle/nbody_port.c,
+// port_morton_one): cell corners -B + k * 2B / 2^level are exact in fp64, so the digits are the
+// ones Octree::Add's Contains() tests select.  Bodies outside the root get the key ~0.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long spread3(unsigned int v)
+{
+    unsigned long long x = v & 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
 }
+
+__device__ __forceinline__ unsigned int axis_cell(double p, double B)
+{
+    double lo = -B, size = 2.0 * B;
+    unsigned int q = 0;
+#pragma unroll
+    for (int l = 0; l < kLevels; ++l)
+    {
+        size *= 0.5;
+        const double mid = lo + size;
+        const bool up = p >= mid;
+        q = (q << 1) | (up ? 1u : 0u);
+        if (up) lo = mid;
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(256)
+k_morton(const float4* __restrict__ posw, int n, double B, unsigned long long* __restrict__ keys,
+         unsigned int* __restrict__ vals, unsigned int* __restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool inside = false;
+    if (i < n)
+    {
+        const float4 p = posw[i];
+        const float b = (float)B;
+        inside = p.x >= -b && p.y >= -b && p.z >= -b && p.x < b && p.y < b && p.z < b;
+        unsigned long long key = kOutside;
+        if (inside)
+        {
+            const unsigned int qx = axis_cell((double)p.x, B), qy = axis_cell((double)p.y, B), qz = axis_cell((double)p.z, B);
+            key = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+        }
+        keys[i] = key;
+        vals[i] = (unsigned int)i;
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, inside);
+    if ((threadIdx.x & 31) == 0 && mask) atomicAdd(&counters[C_INBOUNDS], __popc(mask));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: stable LSD radix sort, 8 bits per pass, (key 64, value 32).  Hand-rolled, no CUB.
+// Per pass: block histograms -> exclusive scan in (digit, block) order -> stable scatter.
+// A block owns a contiguous tile; warp w owns a contiguous 512-key chunk of it and walks it in
+// rounds of 32 consecutive keys, so the order (block, warp, round, lane) is the input order.
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const unsigned long long* __restrict__ keys, int n, int shift, unsigned int* __restrict__ hist, int tiles)
+{
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const int i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(unsigned int)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// one block per digit: in-place exclusive scan of the digit's row, total to totals[digit]
+__global__ void __launch_bounds__(256)
+k_rs_scan_rows(unsigned int* __restrict__ hist, int tiles, unsigned int* __restrict__ totals)
+{
+    __shared__ unsigned int warp_sums[8];
+    __shared__ unsigned int carry;
+    unsigned int* row = hist + (size_t)blockIdx.x * tiles;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 256)
+    {
+        const int i = base + threadIdx.x;
+        const unsigned int v = i < tiles ? row[i] : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned int wprefix = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += warp_sums[w];
+        const unsigned int c = carry;
+        if (i < tiles) row[i] = c + wprefix + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c + wprefix + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_rs_scan_totals(unsigned int* __restrict__ totals)
+{
+    __shared__ unsigned int s[256];
+    s[threadIdx.x] = totals[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned int run = 0;
+        for (int d = 0; d < 256; ++d) { const unsigned int v = s[d]; s[d] = run; run += v; }
+    }
+    __syncthreads();
+    totals[threadIdx.x] = s[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+             unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
+             const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals, int tiles)
+{
+    __shared__ unsigned int wh[RS_WARPS][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
+    __syncthreads();
+
+    const int chunk = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+    unsigned long long key[RS_ITEMS];
+    unsigned int val[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const int i = chunk + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0ull;
+        val[r] = ok ? vals_in[i] : 0u;
+        // invalid lanes get a private pseudo-digit so they never match anyone
+        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & 255u) : (256u + lane);
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        if (ok && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int d = threadIdx.x;   // RS_THREADS == 256 digits
+        unsigned int run = totals[d] + hist[(size_t)d * tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { const unsigned int c = wh[w][d]; wh[w][d] = run; run += c; }
+    }
+    __syncthreads();
+    const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const int i = chunk + r * 32 + lane;
+        const bool ok = i < n;
+        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & 255u) : (256u + lane);
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        unsigned int pos = 0;
+        if (ok) pos = wh[warp][d] + __popc(peers & lt);
+        __syncwarp();
+        if (ok)
+        {
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+            if (lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: Karras radix tree (HPG 2012, section 3) over the m sorted in-bounds keys.
+// Node ids: internal node i -> i, leaf slot j -> leaf_base + j.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta_fn(const unsigned long long* __restrict__ k, int m, int i, int j)
+{
+    if (j < 0 || j >= m) return -1;
+    const unsigned long long x = k[i] ^ k[j];
+    if (x != 0ull) return __clzll((long long)x);
+    return 64 + __clz(i ^ j);
+}
+
+__global__ void __launch_bounds__(256)
+k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ counters, int leaf_base,
+         int* __restrict__ child_l, int* __restrict__ child_r, int* __restrict__ prefix, int* __restrict__ parent,
+         unsigned int* __restrict__ flags)
+{
+    const int m = (int)counters[C_INBOUNDS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m - 1) return;
+    const int d = (delta_fn(keys, m, i, i + 1) - delta_fn(keys, m, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta_fn(keys, m, i, i - d);
+    int lmax = 2;
+    while (delta_fn(keys, m, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_fn(keys, m, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta_fn(keys, m, i, j);
+    int s = 0, t = l;
+    do
+    {
+        t = (t + 1) / 2;
+        if (delta_fn(keys, m, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int cl = (lo == gamma) ? leaf_base + gamma : gamma;
+    const int cr = (hi == gamma + 1) ? leaf_base + gamma + 1 : gamma + 1;
+    child_l[i] = cl;
+    child_r[i] = cr;
+    prefix[i] = dnode;
+    parent[cl] = i;
+    parent[cr] = i;
+    flags[i] = 0;
+    if (i == 0) parent[0] = kEnd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: bottom-up weight / weighted-position sums in fp64 (Octree::CalculateMass, Octree.cpp:86-105,
+// which accumulates the centre of mass in fp32 and overflows for large total mass -- fp64 here).
+// One thread per leaf climbs; the second arrival at a node combines (left + right).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_node(int id, int leaf_base, const float4* __restrict__ posw,
+                                          const unsigned int* __restrict__ order, const double* nw,
+                                          const double* ns, size_t plane, double& w, double& sx,
+                                          double& sy, double& sz)
+{
+    if (id >= leaf_base)
+    {
+        const float4 p = posw[order[id - leaf_base]];
+        w = (double)p.w;
+        sx = w * (double)p.x; sy = w * (double)p.y; sz = w * (double)p.z;
+    }
+    else
+    {
+        // written by another SM earlier in this kernel: read through L2, never a stale L1 line
+        w = __ldcg(nw + id);
+        sx = __ldcg(ns + id); sy = __ldcg(ns + plane + id); sz = __ldcg(ns + 2 * plane + id);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ order,
+            const unsigned int* __restrict__ counters, int leaf_base, const int* __restrict__ child_l,
+            const int* __restrict__ child_r, const int* __restrict__ parent, unsigned int* __restrict__ flags,
+            double* nw, double* ns, size_t plane)
+{
+    const int m = (int)counters[C_INBOUNDS];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m || m < 2) return;
+    int node = parent[leaf_base + j];
+    while (node != kEnd)
+    {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1u) == 0u) return;   // first arrival: the sibling subtree is not done
+        __threadfence();
+        double wl, lx, ly, lz, wr, rx, ry, rz;
+        load_node(child_l[node], leaf_base, posw, order, nw, ns, plane, wl, lx, ly, lz);
+        load_node(child_r[node], leaf_base, posw, order, nw, ns, plane, wr, rx, ry, rz);
+        nw[node] = wl + wr;
+        ns[node] = lx + rx;
+        ns[plane + node] = ly + ry;
+        ns[2 * plane + node] = lz + rz;
+        node = parent[node];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6b: traversal records.  a = {com.xyz, G M 2^-27}, b = {open threshold, next-if-opened,
+// next-if-skipped, body}.  Threshold: leaves -1 (always evaluated), owning nodes (width/theta)^2,
+// nodes that own no octree cell are skipped by the pointers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int level_of(int prefix_bits)
+{
+    return prefix_bits >= 64 ? kLevels : min(kLevels, (prefix_bits - 1) / 3);
+}
+
+__device__ __forceinline__ bool owns_cell(int id, const int* __restrict__ prefix, const int* __restrict__ parent)
+{
+    const int p = parent[id];
+    if (p == kEnd) return true;
+    return level_of(prefix[id]) > level_of(prefix[p]);
+}
+
+__device__ __forceinline__ int enter_subtree(int id, int leaf_base, const int* __restrict__ child_l,
+                                             const int* __restrict__ prefix, const int* __restrict__ parent)
+{
+    while (id < leaf_base && !owns_cell(id, prefix, parent)) id = child_l[id];
+    return id;
+}
+
+__device__ __forceinline__ int after_subtree(int id, int leaf_base, const int* __restrict__ child_l,
+                                             const int* __restrict__ child_r, const int* __restrict__ prefix,
+                                             const int* __restrict__ parent)
+{
+    for (;;)
+    {
+        const int p = parent[id];
+        if (p == kEnd) return kEnd;
+        if (child_l[p] == id) return enter_subtree(child_r[p], leaf_base, child_l, prefix, parent);
+        id = p;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ order, unsigned int* __restrict__ counters,
+           int leaf_base, const int* __restrict__ child_l, const int* __restrict__ child_r,
+           const int* __restrict__ prefix, const int* __restrict__ parent, const double* __restrict__ nw,
+           const double* __restrict__ ns, size_t plane, float root_width, float inv_theta,
+           float4* __restrict__ walk_a, int4* __restrict__ walk_b)
+{
+    const int m = (int)counters[C_INBOUNDS];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) counters[C_START] = (unsigned int)(m >= 2 ? 0 : (m == 1 ? leaf_base : kEnd));
+    if (t < m)
+    {
+        // leaf slot t
+        const int id = leaf_base + t;
+        const unsigned int body = order[t];
+        const float4 p = posw[body];
+        const int nxt = m >= 2 ? after_subtree(id, leaf_base, child_l, child_r, prefix, parent) : kEnd;
+        walk_a[id] = make_float4(p.x, p.y, p.z, p.w * kPreScale);
+        walk_b[id] = make_int4(__float_as_int(-1.0f), nxt, nxt, (int)body);
+    }
+    if (t < m - 1)
+    {
+        const int id = t;
+        if (!owns_cell(id, prefix, parent)) return;   // never visited
+        const double w = nw[id];
+        const double inv = w != 0.0 ? 1.0 / w : 0.0;
+        const float width = ldexpf(root_width, -level_of(prefix[id]));
+        const float lim = width * inv_theta;
+        walk_a[id] = make_float4((float)(ns[id] * inv), (float)(ns[plane + id] * inv), (float)(ns[2 * plane + id] * inv),
+                                 (float)w * kPreScale);
+        walk_b[id] = make_int4(__float_as_int(lim * lim), enter_subtree(child_l[id], leaf_base, child_l, prefix, parent),
+                               after_subtree(id, leaf_base, child_l, child_r, prefix, parent), -1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: warp-cooperative stackless traversal.  A warp owns 32 consecutive targets of the Morton-
+// sorted list and walks the union of what its lanes need; node records are warp-uniform loads.
+// Every lane applies its OWN acceptance test (the reference's per-particle decisions, not a
+// group criterion): a lane that accepts a cell the warp still has to open for another lane parks
+// until the walk leaves that subtree (the walk reaches `next-if-skipped` of the accepted node).
+// Interaction: same law as all-pairs, a += G M (c - p) / (|d| (d^2 + S)); the self term and
+// coincident bodies vanish through the epsilon (see allpairs.cuh).
+// ------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(256)
+k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ tlist,
+       int ntargets, const unsigned int* __restrict__ counters, const float4* __restrict__ walk_a,
+       const int4* __restrict__ walk_b, int first, int count, float sc, double* __restrict__ acc,
+       unsigned long long* __restrict__ stats)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < ntargets;
+    unsigned int body = 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid)
+    {
+        body = order[tlist ? tlist[t] : (unsigned int)t];
+        p = posw[body];
+    }
+    int cur = (int)counters[C_START];
+    int parked = kNone;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    unsigned int n_cells = 0, n_leaves = 0, n_visits = 0;
+    while (cur != kEnd)
+    {
+        const float4 a = walk_a[cur];
+        const int4 b = walk_b[cur];
+        if (parked == cur) parked = kNone;
+        const bool active = valid && parked == kNone;
+        const float dx = a.x - p.x, dy = a.y - p.y, dz = a.z - p.z;
+        float d2 = dx * dx;
+        d2 = fmaf(dy, dy, d2);
+        d2 = fmaf(dz, dz, d2);
+        const float thr = __int_as_float(b.x);
+        const bool accept = d2 > thr;
+        const bool use = active && accept;
+        const float tt = fmaf(d2, kPreScale, sc);
+        const float u = d2 * tt;
+        const float x = fmaf(u, tt, kEps);
+        const float s = use ? a.w * rsqrt_approx(x) : 0.f;
+        ax = fmaf(s, dx, ax);
+        ay = fmaf(s, dy, ay);
+        az = fmaf(s, dz, az);
+        if (use) parked = b.z;
+        if (STATS && active)
+        {
+            ++n_visits;
+            if (accept) { if (thr < 0.f) n_leaves += ((unsigned int)b.w != body); else ++n_cells; }
+        }
+        const bool open = __any_sync(0xffffffffu, active && !accept);
+        cur = open ? b.y : b.z;
+    }
+    if (valid)
+    {
+        const int li = (int)body - first;
+        if (li >= 0 && li < count)
+        {
+            acc[li] = (double)ax;
+            acc[(size_t)count + li] = (double)ay;
+            acc[2 * (size_t)count + li] = (double)az;
+        }
+    }
+    if (STATS)
+    {
+        unsigned long long c = n_cells, l = n_leaves, v = n_visits;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            c += __shfl_down_sync(0xffffffffu, c, o);
+            l += __shfl_down_sync(0xffffffffu, l, o);
+            v += __shfl_down_sync(0xffffffffu, v, o);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[0], c); atomicAdd(&stats[1], l); atomicAdd(&stats[2], v); }
+    }
+}
+
+// Owned targets in Morton order (world > 1): slots whose body index lies in [first, first+count).
+__global__ void __launch_bounds__(256)
+k_select_flags(const unsigned int* __restrict__ order, int n, int first, int count, unsigned int* __restrict__ flag)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n)
+    {
+        const int b = (int)order[s] - first;
+        flag[s] = (b >= 0 && b < count) ? 1u : 0u;
+    }
+}
+
+// Exclusive scan of flag[] -> positions, compaction.  One block per 4096 slots + row scan reuse.
+__global__ void __launch_bounds__(256)
+k_block_sums(const unsigned int* __restrict__ flag, int n, unsigned int* __restrict__ sums)
+{
+    __shared__ unsigned int s[256];
+    unsigned int c = 0;
+    const int base = blockIdx.x * 4096;
+    for (int k = 0; k < 16; ++k)
+    {
+        const int i = base + k * 256 + threadIdx.x;
+        if (i < n) c += flag[i];
+    }
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1)
+    {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = s[0];
+}
+
+__global__ void __launch_bounds__(256)
+k_compact(const unsigned int* __restrict__ flag, int n, const unsigned int* __restrict__ block_prefix,
+          unsigned int* __restrict__ tlist)
+{
+    __shared__ unsigned int warp_sums[8];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = block_prefix[blockIdx.x];
+    __syncthreads();
+    const int base = blockIdx.x * 4096;
+    for (int k = 0; k < 16; ++k)
+    {
+        const int i = base + k * 256 + threadIdx.x;
+        const unsigned int v = i < n ? flag[i] : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned int wprefix = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += warp_sums[w];
+        const unsigned int c = carry;
+        if (v) tlist[c + wprefix + x - 1] = (unsigned int)i;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c + wprefix + x;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+void tree_release(nb_sim* h)
+{
+    TreeBuffers& t = h->tree;
+    for (int k = 0; k < 2; ++k) { cudaFree(t.keys[k]); cudaFree(t.vals[k]); t.keys[k] = nullptr; t.vals[k] = nullptr; }
+    cudaFree(t.hist); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
+    cudaFree(t.range); cudaFree(t.flags); cudaFree(t.nmass); cudaFree(t.ncom); cudaFree(t.walk_a);
+    cudaFree(t.walk_b); cudaFree(t.stats);
+    t = TreeBuffers();
+}
+
+int tree_reserve(nb_sim* h)
+{
+    TreeBuffers& t = h->tree;
+    const size_t n = h->n;
+    if (t.capacity >= n) return NB_OK;
+    tree_release(h);
+    const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
+    for (int k = 0; k < 2; ++k)
+    {
+        NB_CUDA(cudaMalloc(&t.keys[k], n * sizeof(unsigned long long)));
+        NB_CUDA(cudaMalloc(&t.vals[k], n * sizeof(unsigned int)));
+    }
+    t.hist_words = 256 * tiles + 256 + tiles + 16;
+    NB_CUDA(cudaMalloc(&t.hist, t.hist_words * sizeof(unsigned int)));
+    NB_CUDA(cudaMalloc(&t.counters, C_WORDS * sizeof(unsigned int)));
+    NB_CUDA(cudaMalloc(&t.child, 2 * n * sizeof(int)));
+    NB_CUDA(cudaMalloc(&t.parent, 2 * n * sizeof(int)));
+    NB_CUDA(cudaMalloc(&t.prefix, n * sizeof(int)));
+    NB_CUDA(cudaMalloc(&t.range, n * sizeof(unsigned int)));          // target-selection flags / list
+    NB_CUDA(cudaMalloc(&t.flags, n * sizeof(unsigned int)));
+    NB_CUDA(cudaMalloc(&t.nmass, n * sizeof(double)));
+    NB_CUDA(cudaMalloc(&t.ncom, 3 * n * sizeof(double)));
+    NB_CUDA(cudaMalloc(&t.walk_a, 2 * n * sizeof(float4)));
+    NB_CUDA(cudaMalloc(&t.walk_b, 2 * n * sizeof(int4)));
+    NB_CUDA(cudaMalloc(&t.stats, 3 * sizeof(unsigned long long)));
+    NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), h->stream));
+    t.capacity = n;
+    return NB_OK;
+}
+
+int tree_build(nb_sim* h)
+{
+    NB_CHECK(tree_reserve(h));
+    TreeBuffers& t = h->tree;
+    const int n = (int)h->n;
+    const int tiles = (n + RS_TILE - 1) / RS_TILE;
+    cudaStream_t st = h->stream;
+
+    NB_CUDA(cudaMemsetAsync(t.counters, 0, C_WORDS * sizeof(unsigned int), st));
+    k_morton<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, t.keys[0], t.vals[0], t.counters);
+    ++h->last_launches;
+
+    unsigned int* totals = t.hist + (size_t)256 * tiles;
+    int src = 0;
+    for (int pass = 0; pass < 8; ++pass)
+    {
+        const int shift = 8 * pass;
+        k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], n, shift, t.hist, tiles);
+        k_rs_scan_rows<<<256, 256, 0, st>>>(t.hist, tiles, totals);
+        k_rs_scan_totals<<<1, 256, 0, st>>>(totals);
+        k_rs_scatter<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, shift,
+                                                  t.hist, totals, tiles);
+        h->last_launches += 4;
+        src ^= 1;
+    }
+    t.cur = src;
+    NB_CUDA(cudaGetLastError());
+
+    const int leaf_base = n;
+    int* child_l = t.child;
+    int* child_r = t.child + n;
+    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, child_l, child_r, t.prefix, t.parent, t.flags);
+    k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, child_l, child_r, t.parent,
+                                                   t.flags, t.nmass, t.ncom, (size_t)n);
+    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, child_l, child_r, t.prefix,
+                                                  t.parent, t.nmass, t.ncom, (size_t)n, 2.0f * h->cfg.bounds,
+                                                  1.0f / h->cfg.theta, t.walk_a, t.walk_b);
+    h->last_launches += 3;
+    NB_CUDA(cudaGetLastError());
+    t.built = true;
+    return NB_OK;
+}
+
+static bool g_walk_stats = false;
+
+int tree_walk(nb_sim* h)
+{
+    TreeBuffers& t = h->tree;
+    const int n = (int)h->n;
+    cudaStream_t st = h->stream;
+    const unsigned int* order = t.vals[t.cur];
+    const unsigned int* tlist = nullptr;
+    int ntargets = n;
+    if (h->cfg.world > 1)
+    {
+        // owned bodies in Morton order: flags -> block sums -> scan -> compaction
+        const int blocks = (n + 4095) / 4096;
+        unsigned int* flag = t.flags;                 // free again after the bottom-up pass
+        unsigned int* sums = t.hist;                  // radix-sort scratch is free here
+        unsigned int* total = t.hist + blocks;
+        k_select_flags<<<blocks_for(n, 256), 256, 0, st>>>(order, n, (int)h->first, (int)h->count, flag);
+        k_block_sums<<<blocks, 256, 0, st>>>(flag, n, sums);
+        k_rs_scan_rows<<<1, 256, 0, st>>>(sums, blocks, total);
+        k_compact<<<blocks, 256, 0, st>>>(flag, n, sums, reinterpret_cast<unsigned int*>(t.range));
+        h->last_launches += 4;
+        tlist = reinterpret_cast<const unsigned int*>(t.range);
+        ntargets = (int)h->count;
+    }
+    const float sc = (float)(h->cfg.softening * (double)kPreScale);
+    if (g_walk_stats)
+    {
+        NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), st));
+        k_walk<true><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, t.walk_b,
+                                                              (int)h->first, (int)h->count, sc, h->acc, t.stats);
+    }
+    else
+    {
+        k_walk<false><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, t.walk_b,
+                                                               (int)h->first, (int)h->count, sc, h->acc, t.stats);
+    }
+    ++h->last_launches;
+    NB_CUDA(cudaGetLastError());
+    return NB_OK;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
 extern "C" {
-int nb_get_morton(nb_handle, uint64_t*, uint32_t*, size_t*) { nb::set_error("not built yet"); return NB_ERR_STATE; }
-int nb_get_tree(nb_handle, int32_t*, int32_t*, int32_t*, double*, float*, size_t*) { nb::set_error("not built yet"); return NB_ERR_STATE; }
-int nb_get_walk_stats(nb_handle, uint64_t*) { nb::set_error("not built yet"); return NB_ERR_STATE; }
+
+int nb_get_morton(nb_handle h, uint64_t* codes, uint32_t* order, size_t* n_inbounds)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(h->cfg.mode == NB_MODE_BARNESHUT, NB_ERR_STATE, "handle is not in Barnes-Hut mode");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->tree.built) NB_CHECK(tree_build(h));
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned int m = 0;
+    NB_CUDA(cudaMemcpy(&m, h->tree.counters + C_INBOUNDS, sizeof(m), cudaMemcpyDeviceToHost));
+    if (n_inbounds) *n_inbounds = m;
+    if (codes) NB_CUDA(cudaMemcpy(codes, h->tree.keys[h->tree.cur], (size_t)m * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (order) NB_CUDA(cudaMemcpy(order, h->tree.vals[h->tree.cur], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return NB_OK;
 }
+
+int nb_get_tree(nb_handle h, int32_t* left, int32_t* right, int32_t* prefix_bits, double* mass, float* com3, size_t* n_internal)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(h->cfg.mode == NB_MODE_BARNESHUT, NB_ERR_STATE, "handle is not in Barnes-Hut mode");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->tree.built) NB_CHECK(tree_build(h));
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned int m = 0;
+    NB_CUDA(cudaMemcpy(&m, h->tree.counters + C_INBOUNDS, sizeof(m), cudaMemcpyDeviceToHost));
+    const size_t k = m >= 2 ? m - 1 : 0;
+    if (n_internal) *n_internal = k;
+    if (k == 0) return NB_OK;
+    const size_t n = h->n;
+    const int leaf_base = (int)n;
+    std::vector<int> tmp(k);
+    for (int side = 0; side < 2; ++side)
+    {
+        int32_t* dst = side == 0 ? left : right;
+        if (!dst) continue;
+        NB_CUDA(cudaMemcpy(tmp.data(), h->tree.child + side * n, k * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < k; ++i) dst[i] = tmp[i] >= leaf_base ? ~(tmp[i] - leaf_base) : tmp[i];
+    }
+    if (prefix_bits) NB_CUDA(cudaMemcpy(prefix_bits, h->tree.prefix, k * sizeof(int), cudaMemcpyDeviceToHost));
+    if (mass || com3)
+    {
+        std::vector<double> w(k), s(3 * k);
+        NB_CUDA(cudaMemcpy(w.data(), h->tree.nmass, k * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < 3; ++c)
+            NB_CUDA(cudaMemcpy(s.data() + c * k, h->tree.ncom + c * n, k * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < k; ++i)
+        {
+            if (mass) mass[i] = w[i] / h->cfg.G;
+            if (com3)
+                for (int c = 0; c < 3; ++c) com3[3 * i + c] = (float)(w[i] != 0.0 ? s[c * k + i] / w[i] : 0.0);
+        }
+    }
+    return NB_OK;
+}
+
+int nb_get_walk_stats(nb_handle h, uint64_t stats3[3])
+{
+    NB_REQUIRE(h != nullptr && stats3 != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->cfg.mode == NB_MODE_BARNESHUT, NB_ERR_STATE, "handle is not in Barnes-Hut mode");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    // one instrumented traversal of the current tree (the production walk carries no counters)
+    NB_REQUIRE(h->exchanged, NB_ERR_STATE, "positions of remote ranks are stale");
+    NB_CHECK(tree_build(h));
+    g_walk_stats = true;
+    const int rc = tree_walk(h);
+    g_walk_stats = false;
+    NB_CHECK(rc);
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned long long s[3];
+    NB_CUDA(cudaMemcpy(s, h->tree.stats, sizeof(s), cudaMemcpyDeviceToHost));
+    stats3[0] = s[0]; stats3[1] = s[1]; stats3[2] = s[2];
+    return NB_OK;
+}
+
+}  // extern "C"

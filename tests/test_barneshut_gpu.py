@@ -1,0 +1,263 @@
+"""Barnes-Hut CUDA path against the oracle, through the C ABI.  GPU only (pytest -m gpu).
+
+BASELINE.json north_star: Morton codes and tree topology bit-exact (against the CPU restatement,
+which tests/test_oracle.py ties to the reference octree); accelerations within 1e-3 MEDIAN relative
+at matched theta."""
+import numpy as np
+import pytest
+
+from conftest import as_particles, load_golden, rel_err
+from oracle import checker, port
+
+pytestmark = pytest.mark.gpu
+
+BH_MEDIAN_RTOL = 1e-3
+
+
+def bh(pkg, theta=0.5, **kw):
+    return pkg.Sim(mode=pkg.MODE_BARNESHUT, theta=theta, **kw)
+
+
+@pytest.fixture(scope="module")
+def galaxy(pkg):
+    return pkg.seed_galaxy_host(1024, 42, 1.0)
+
+
+def scattered(pkg, n, seed, spread=3000.0, outside=0.1, duplicates=True):
+    """Bodies filling the root cube, a fraction outside it, some on cell boundaries, some duplicated."""
+    rng = np.random.default_rng(seed)
+    p = np.zeros(n, dtype=pkg.PARTICLE_DTYPE)
+    p["Position"] = rng.uniform(-spread, spread, (n, 3)).astype(np.float32)
+    k = int(outside * n)
+    p["Position"][:k] *= 2.0                                   # many of these leave [-4000, 4000)
+    p["Position"][k:k + 8] = [[0, 0, 0], [-4000, -4000, -4000], [2000, -2000, 1000], [4000, 0, 0],
+                              [1.5, 1.5, 1.5], [1.5, 1.5, 1.5], [-0.0, 125.0, 3999.9998], [1e-30, -1e-30, 0]]
+    if not duplicates:
+        p["Position"][k + 5] = [1.5, 1.5, 1.75]
+    p["Mass"] = rng.uniform(1e28, 1e30, n)
+    p["Velocity"] = rng.normal(0, 1e15, (n, 3))
+    return p
+
+
+def test_morton_codes_and_order_bit_exact(pkg, galaxy):
+    for p in (galaxy, scattered(pkg, 5000, 1), scattered(pkg, 4097, 2, spread=10.0)):
+        sim = bh(pkg)
+        sim.init(p)
+        codes, order = sim.morton()
+        want_codes, want_order = port.morton_sorted(p)
+        assert len(codes) == len(want_codes)
+        assert np.array_equal(codes, want_codes)
+        assert np.array_equal(order, want_order)               # stable: ties keep body order
+        sim.close()
+
+
+def test_morton_codes_match_reference_octree_paths(pkg, galaxy):
+    g = load_golden("barneshut_n1024.npz")
+    sim = bh(pkg)
+    sim.init(galaxy)
+    codes, order = sim.morton()
+    depth = g["leaf_depth"][order]
+    top = codes >> (np.uint64(3) * (21 - depth).astype(np.uint64))
+    assert np.array_equal(top, g["path"][order])
+    sim.close()
+
+
+def test_radix_tree_topology_bit_exact(pkg, galaxy):
+    for p in (galaxy, scattered(pkg, 5000, 3), scattered(pkg, 777, 4, spread=1.0)):
+        sim = bh(pkg)
+        sim.init(p)
+        codes, _ = sim.morton()
+        t = sim.tree()
+        left, right, prefix = port.karras(codes)
+        assert np.array_equal(t["left"], left)
+        assert np.array_equal(t["right"], right)
+        assert np.array_equal(t["prefix"], prefix)
+        sim.close()
+
+
+def test_node_masses_and_centres_match_reference_cells(pkg, galaxy):
+    """Radix-tree nodes that own an octree cell carry that cell's mass / centre of mass
+    (Octree::CalculateMass, Octree.cpp:86-105; the reference accumulates the centre in fp32)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("needs oracle/_ref")
+    sim = bh(pkg)
+    sim.init(galaxy)
+    codes, order = sim.morton()
+    t = sim.tree()
+    level = np.where(t["prefix"] >= 64, 21, np.minimum(21, (t["prefix"] - 1) // 3))
+    parent_level = np.full(len(level), -1)
+    for side in ("left", "right"):
+        kids = t[side]
+        internal = kids >= 0
+        parent_level[kids[internal]] = level[internal]
+    checked = 0
+    for i in range(0, len(level), 3):
+        if level[i] <= parent_level[i]:
+            continue                                            # owns no octree cell (never visited)
+        # first leaf under node i gives the cell's path
+        node = i
+        while node >= 0:
+            node = t["left"][node]
+        slot = ~node
+        L = int(level[i])
+        path = int(codes[slot]) >> (3 * (21 - L))
+        cell = ref.octree_cell(galaxy, L, path)
+        assert cell is not None
+        mass, com, count, width = cell
+        assert count >= 2 and width == 8000.0 / (1 << L)
+        assert abs(t["mass"][i] - mass) <= 1e-6 * mass          # G m rounded to fp32 per body
+        assert np.abs(t["com"][i] - com).max() <= 5e-3
+        checked += 1
+    assert checked > 100
+    sim.close()
+
+
+def test_accelerations_match_reference_theta_half(pkg, galaxy):
+    g = load_golden("barneshut_n1024.npz")
+    sim = bh(pkg, theta=0.5)
+    sim.init(galaxy)
+    acc = sim.accelerations()
+    want = g["forces"] / galaxy["Mass"][:, None]
+    err = rel_err(acc, want)
+    print("BH theta=0.5 n=1024 rel err: median %.2e p99 %.2e max %.2e" % (np.median(err), np.quantile(err, 0.99), err.max()))
+    assert np.median(err) < BH_MEDIAN_RTOL
+    assert np.quantile(err, 0.99) < 1e-2
+    # identical acceptance decisions => identical pair-evaluation count
+    stats = sim.walk_stats()
+    assert abs(stats["leaf_evals"] - int(g["work"][1])) <= 2e-3 * int(g["work"][1])
+    sim.close()
+
+
+@pytest.mark.parametrize("theta", [0.3, 1.0, 2.0])
+def test_accelerations_other_thetas(pkg, theta):
+    p = pkg.seed_galaxy_host(3000, 9, 1.0)
+    sim = bh(pkg, theta=theta)
+    sim.init(p)
+    acc = sim.accelerations()
+    t = np.arange(0, 3000, 3)
+    want = checker.barneshut_accel(p, theta, t)
+    err = rel_err(acc[t], want)
+    print("BH theta=%.1f rel err: median %.2e p99 %.2e" % (theta, np.median(err), np.quantile(err, 0.99)))
+    assert np.median(err) < BH_MEDIAN_RTOL
+    sim.close()
+
+
+def test_set_theta_matches_fresh_handle(pkg, galaxy):
+    a = bh(pkg, theta=2.0)
+    a.init(galaxy)
+    a.accelerations()
+    a.set_theta(0.5)                     # BHThetaChanged -> Octree::Theta (BarnesHut.cpp:29-31)
+    b = bh(pkg, theta=0.5)
+    b.init(galaxy)
+    assert np.array_equal(a.accelerations(), b.accelerations())
+    a.close()
+    b.close()
+
+
+def test_out_of_bounds_bodies(pkg):
+    """Bodies outside the root cube are dropped as sources but still receive forces
+    (Octree.cpp:58-62, BarnesHut.cpp:103-110)."""
+    # no exactly coincident bodies here: the reference splits them until the cell size underflows
+    # to zero and then loses both (and their mass) -- SURVEY.md appendix A, "do not replicate" 3;
+    # this engine keeps them as a bucket at the finest Morton level (test_edge_cases).
+    p = scattered(pkg, 4000, 5, duplicates=False)
+    sim = bh(pkg, theta=0.5)
+    sim.init(p)
+    acc = sim.accelerations()
+    t = np.arange(0, 4000, 4)
+    want = checker.barneshut_accel(p, 0.5, t)
+    ok = np.linalg.norm(want, axis=1) > 0
+    err = rel_err(acc[t][ok], want[ok])
+    assert np.median(err) < BH_MEDIAN_RTOL
+    outside = (np.abs(p["Position"]) >= 4000).any(axis=1) | (p["Position"] < -4000).any(axis=1)
+    assert outside.sum() > 100 and np.all(np.isfinite(acc))
+    assert np.all(np.linalg.norm(acc[outside], axis=1) > 0)
+    codes, order = sim.morton()
+    assert len(codes) == 4000 - int(((p["Position"] < -4000) | (p["Position"] >= 4000)).any(axis=1).sum())
+    sim.close()
+
+
+def test_five_steps_against_golden(pkg, galaxy):
+    g = load_golden("barneshut_n1024.npz")
+    want = as_particles(g["state5"], pkg.PARTICLE_DTYPE)
+    sim = bh(pkg, theta=0.5)
+    sim.init(galaxy)
+    sim.step(float(g["dt"]), 5)
+    q = galaxy.copy()
+    sim.read(q)
+    dv_want = want["Velocity"] - galaxy["Velocity"]
+    err = np.linalg.norm(q["Velocity"] - want["Velocity"], axis=1) / np.linalg.norm(dv_want, axis=1)
+    print("BH 5 steps dv rel err: median %.2e p99 %.2e" % (np.median(err), np.quantile(err, 0.99)))
+    assert np.median(err) < BH_MEDIAN_RTOL
+    assert np.abs(q["Position"] - want["Position"]).max() < 1e-3
+    # BarnesHut leaves the last force in Particle::Forces (BarnesHut.cpp:75,108)
+    ferr = rel_err(q["Forces"], want["Forces"])
+    assert np.median(ferr) < BH_MEDIAN_RTOL
+    assert np.array_equal(q["Colour"], galaxy["Colour"])
+    sim.close()
+
+
+def test_edge_cases(pkg):
+    dt = pkg.PARTICLE_DTYPE
+    sim = bh(pkg, theta=0.5)
+    # a single body; two bodies; everything outside the root; exact duplicates
+    p = np.zeros(1, dtype=dt); p["Mass"] = 1e30
+    sim.init(p)
+    assert np.all(sim.accelerations() == 0)
+    p = np.zeros(2, dtype=dt); p["Mass"] = (1e30, 2e29); p["Position"][1] = (3, 4, 0)
+    sim.init(p)
+    acc = sim.accelerations()
+    want = port.allpairs_forces(p) / p["Mass"][:, None]
+    assert rel_err(acc, want).max() < 1e-5
+    p = np.zeros(64, dtype=dt); p["Mass"] = 1e30
+    p["Position"] = np.random.default_rng(0).uniform(5000, 9000, (64, 3)).astype(np.float32)
+    sim.init(p)
+    assert np.all(sim.accelerations() == 0)                  # no sources inside the root
+    codes, _ = sim.morton()
+    assert len(codes) == 0
+    p = np.zeros(40, dtype=dt); p["Mass"] = 1e30
+    p["Position"][:20] = (7.25, -3.5, 100.0)                 # 20 coincident bodies (the reference would recurse forever)
+    p["Position"][20:] = np.random.default_rng(1).uniform(-500, 500, (20, 3)).astype(np.float32)
+    sim.init(p)
+    acc = sim.accelerations()
+    want = port.allpairs_forces(p) / p["Mass"][:, None]      # small n: the tree walk opens everything near
+    assert np.all(np.isfinite(acc))
+    assert np.median(rel_err(acc, want)) < 2e-2
+    sim.close()
+
+
+def test_sharded_ranks_reproduce_single_gpu_bitwise(pkg):
+    p = pkg.seed_galaxy_host(6000, 21, 1.0)
+    one = bh(pkg, theta=0.5)
+    one.init(p)
+    acc = one.accelerations()
+    shards = [bh(pkg, theta=0.5, rank=r, world=3) for r in range(3)]
+    for s in shards:
+        s.init(p)
+    got = np.concatenate([s.accelerations() for s in shards])
+    # same tree on every rank; a shard's warps group different targets, which changes which nodes
+    # the WARP opens but neither what a lane accepts nor the order it accumulates in -> bit identical
+    assert np.array_equal(got, acc)
+    for s in shards:
+        s.close()
+    one.close()
+
+
+def test_large_n_sampled_parity(pkg):
+    """configs[3] shape at N = 262144: sampled targets against the reference walk."""
+    n = 1 << 18
+    p = pkg.seed_galaxy_host(n, 42, 1.0)
+    sim = bh(pkg, theta=0.5)
+    sim.init(p)
+    acc = sim.accelerations()
+    t = np.arange(0, n, n // 256)
+    want = checker.barneshut_accel(p, 0.5, t)
+    err = rel_err(acc[t], want)
+    print("BH n=262144 rel err: median %.2e p99 %.2e" % (np.median(err), np.quantile(err, 0.99)))
+    assert np.median(err) < BH_MEDIAN_RTOL
+    # size-independent properties: sorted keys, a permutation, momentum balance
+    codes, order = sim.morton()
+    assert np.all(codes[1:] >= codes[:-1])
+    assert np.array_equal(np.sort(order), np.arange(len(order)))
+    sim.close()
