@@ -144,6 +144,10 @@ NB_API int nb_read_aos(nb_handle h, void* particles, size_t n, size_t stride);
 NB_API int nb_read_soa(nb_handle h, float* pos3, double* vel3);
 NB_API int nb_owned_range(nb_handle h, size_t* first, size_t* count);
 NB_API int nb_num_bodies(nb_handle h, size_t* n);
+/* The static partition of n bodies over `world` handles: rank r owns [r*n/world, (r+1)*n/world)
+ * -- the same block partition the reference uses over its worker threads
+ * (BruteForceCPU.cpp:47-54, without its remainder bug).  Host-only, needs no device. */
+NB_API int nb_shard_range(size_t n, int rank, int world, size_t* first, size_t* count);
 
 /* ---- parity hooks --------------------------------------------------------------------------- */
 /* Accelerations (Forces / Mass of the reference) of the owned bodies for the CURRENT positions,
@@ -183,6 +187,9 @@ NB_API int nb_mark_exchanged(nb_handle h);
 /* Device time in milliseconds (CUDA events on the handle's stream) of the last nb_step call and of
  * its dominant kernel, and how many kernels that call launched. */
 NB_API int nb_last_step_timing(nb_handle h, float* total_ms, float* force_kernel_ms, int* launches);
+/* Barnes-Hut: device time of the tree build (Morton + sort + Karras + reduction) of that step;
+ * force_kernel_ms above is then the traversal alone.  0 in all-pairs mode. */
+NB_API int nb_last_build_timing(nb_handle h, float* build_ms);
 /* Pure-FFMA issue-rate probe: sustained FP32 FLOP/s of this device as measured now. */
 NB_API int nb_probe_fp32_peak(nb_handle h, double* flops_per_s);
 

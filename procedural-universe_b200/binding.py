@@ -92,6 +92,8 @@ def load():
     L.nb_mark_exchanged.argtypes = [vp]
     L.nb_last_step_timing.argtypes = [vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int)]
     L.nb_probe_fp32_peak.argtypes = [vp, C.POINTER(f64)]
+    L.nb_last_build_timing.argtypes = [vp, C.POINTER(f32)]
+    L.nb_shard_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
     _lib = L
     return L
 
@@ -271,6 +273,11 @@ class Sim:
         t, f, k = C.c_float(), C.c_float(), C.c_int()
         _check(self._L.nb_last_step_timing(self._h, C.byref(t), C.byref(f), C.byref(k)))
         return t.value, f.value, k.value
+
+    def last_build_ms(self):
+        t = C.c_float()
+        _check(self._L.nb_last_build_timing(self._h, C.byref(t)))
+        return t.value
 
     def probe_fp32_peak(self):
         v = C.c_double()

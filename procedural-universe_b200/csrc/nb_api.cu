@@ -117,11 +117,24 @@ int launch_allpairs(nb_sim* h)
     return NB_OK;
 }
 
-static int compute_forces(nb_sim* h)
+// `timed`: bracket the dominant kernel (all-pairs kernel / tree walk) with ev[2], ev[3] and the
+// tree build with ev[4], ev[2].
+static int compute_forces(nb_sim* h, bool timed)
 {
-    if (h->cfg.mode == NB_MODE_ALLPAIRS) return launch_allpairs(h);
-    NB_CHECK(tree_build(h));
-    return tree_walk(h);
+    if (timed) NB_CUDA(cudaEventRecord(h->ev[4], h->stream));
+    if (h->cfg.mode == NB_MODE_ALLPAIRS)
+    {
+        if (timed) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        NB_CHECK(launch_allpairs(h));
+    }
+    else
+    {
+        NB_CHECK(tree_build(h));
+        if (timed) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        NB_CHECK(tree_walk(h));
+    }
+    if (timed) NB_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    return NB_OK;
 }
 
 static int set_bodies(nb_sim* h, size_t n)
@@ -230,7 +243,7 @@ int nb_create(const nb_config* cfg, nb_handle* out)
         if (e == cudaSuccess) e = cudaMemset(h->wmax, 0, sizeof(float));
         if (e != cudaSuccess) { nb::set_error("cudaMalloc: %s", cudaGetErrorString(e)); nb_destroy(h); return NB_ERR_CUDA; }
     }
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
     {
         cudaError_t e = cudaEventCreate(&h->ev[i]);
         if (e != cudaSuccess) { nb::set_error("cudaEventCreate: %s", cudaGetErrorString(e)); nb_destroy(h); return NB_ERR_CUDA; }
@@ -248,7 +261,7 @@ int nb_destroy(nb_handle h)
     free_state(h);
     cudaFree(h->d_aos);
     cudaFree(h->wmax);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -322,9 +335,7 @@ int nb_step(nb_handle h, float dt, int nsteps)
         NB_REQUIRE(h->exchanged, NB_ERR_STATE,
                    "world > 1 without nb_comm_init: call nb_mark_exchanged after exchanging positions");
         const bool last = (s == nsteps - 1);
-        if (last) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        NB_CHECK(compute_forces(h));
-        if (last) NB_CUDA(cudaEventRecord(h->ev[3], h->stream));
+        NB_CHECK(compute_forces(h, last));
         NB_CHECK(launch_kick_drift(h, dt));
         h->acc_valid = false;
         h->forces_from_last_step = true;
@@ -444,6 +455,15 @@ int nb_owned_range(nb_handle h, size_t* first, size_t* count)
     return NB_OK;
 }
 
+int nb_shard_range(size_t n, int rank, int world, size_t* first, size_t* count)
+{
+    NB_REQUIRE(world >= 1 && rank >= 0 && rank < world, NB_ERR_ARG, "bad rank/world");
+    const size_t f = (size_t)rank * n / (size_t)world;
+    if (first) *first = f;
+    if (count) *count = ((size_t)rank + 1) * n / (size_t)world - f;
+    return NB_OK;
+}
+
 int nb_num_bodies(nb_handle h, size_t* n)
 {
     NB_REQUIRE(h != nullptr && n != nullptr, NB_ERR_ARG, "null argument");
@@ -460,9 +480,7 @@ int nb_compute_accel(nb_handle h)
     h->last_launches = 0;
     h->timing_valid = false;
     NB_CUDA(cudaEventRecord(h->ev[0], h->stream));
-    NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-    NB_CHECK(compute_forces(h));
-    NB_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    NB_CHECK(compute_forces(h, true));
     if (h->cfg.mode == NB_MODE_ALLPAIRS) NB_CHECK(launch_reduce_partials(h));
     NB_CUDA(cudaEventRecord(h->ev[1], h->stream));
     h->timing_valid = true;
@@ -535,6 +553,16 @@ int nb_last_step_timing(nb_handle h, float* total_ms, float* force_kernel_ms, in
     if (total_ms) NB_CUDA(cudaEventElapsedTime(total_ms, h->ev[0], h->ev[1]));
     if (force_kernel_ms) NB_CUDA(cudaEventElapsedTime(force_kernel_ms, h->ev[2], h->ev[3]));
     if (launches) *launches = h->last_launches;
+    return NB_OK;
+}
+
+int nb_last_build_timing(nb_handle h, float* build_ms)
+{
+    NB_REQUIRE(h != nullptr && build_ms != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->timing_valid, NB_ERR_STATE, "no timed call yet");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CUDA(cudaEventSynchronize(h->ev[1]));
+    NB_CUDA(cudaEventElapsedTime(build_ms, h->ev[4], h->ev[2]));
     return NB_OK;
 }
 

@@ -90,7 +90,7 @@ struct nb_sim
     bool forces_from_last_step = false;
     bool exchanged = true;       // posw of remote ranks is current
 
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // step begin/end, force kernel begin/end
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // step begin/end, dominant kernel begin/end, force pass begin
     bool timing_valid = false;
     int last_launches = 0;
     unsigned long long total_launches = 0;
