@@ -132,6 +132,10 @@ NB_API int nb_step(nb_handle h, float dt, int nsteps);
  * caller's AoS array, one step, write Position/Velocity/Forces back, synchronous on return
  * (SimulationState.cpp:52-60 copies the array to a vertex buffer right after Update). */
 NB_API int nb_update_aos(nb_handle h, void* particles, size_t n, size_t stride, float dt);
+/* Page-locks / unlocks a caller-owned host array (cudaHostRegister) so that nb_update_aos copies at
+ * full PCIe rate; optional.  The adapter pins the std::vector it was Init'ed with. */
+NB_API int nb_host_register(void* ptr, size_t bytes);
+NB_API int nb_host_unregister(void* ptr);
 /* Wait for everything queued on the handle's stream. */
 NB_API int nb_sync(nb_handle h);
 

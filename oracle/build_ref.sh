@@ -67,3 +67,19 @@ g++ $CXXFLAGS -shared \
     "$REF/Services/Log.cpp" "$REF/Core/Event.cpp" \
     -o "$OUT/libpu_ref.so"
 echo "build_ref: wrote $OUT/libpu_ref.so"
+
+# The product's C++ adapter (B200Sim : INBodySim) compiled against the same reference headers, plus
+# a driver that runs reference sims and the adapter through the reference's own interface.
+PKG="$HERE/../procedural-universe_b200"
+if [ -f "$PKG/lib/libnbody_b200.so" ]; then
+    g++ $CXXFLAGS -shared \
+        -I"$HERE/ref_shim" -I"$SCRATCH" -I"$REF" -I"$REF/Sim" -I"$HERE/../include" -I"$PKG/host" \
+        "$HERE/adapter_driver.cpp" "$PKG/host/B200Sim.cpp" \
+        "$REF/Sim/BruteForceCPU.cpp" "$REF/Sim/BarnesHut.cpp" "$REF/Sim/Octree.cpp" \
+        "$REF/Services/Log.cpp" "$REF/Core/Event.cpp" \
+        -L"$PKG/lib" -lnbody_b200 -Wl,-rpath,'$ORIGIN/../../procedural-universe_b200/lib' \
+        -o "$OUT/libb200_adapter_test.so"
+    echo "build_ref: wrote $OUT/libb200_adapter_test.so"
+else
+    echo "build_ref: $PKG/lib/libnbody_b200.so not built yet, skipping the adapter test library" >&2
+fi

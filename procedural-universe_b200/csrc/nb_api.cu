@@ -383,6 +383,20 @@ int nb_update_aos(nb_handle h, void* particles, size_t n, size_t stride, float d
     return NB_OK;
 }
 
+int nb_host_register(void* ptr, size_t bytes)
+{
+    NB_REQUIRE(ptr != nullptr && bytes > 0, NB_ERR_ARG, "null argument");
+    NB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return NB_OK;
+}
+
+int nb_host_unregister(void* ptr)
+{
+    NB_REQUIRE(ptr != nullptr, NB_ERR_ARG, "null argument");
+    NB_CUDA(cudaHostUnregister(ptr));
+    return NB_OK;
+}
+
 int nb_sync(nb_handle h)
 {
     NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");

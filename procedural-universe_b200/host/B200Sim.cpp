@@ -1,0 +1,107 @@
+#include "B200Sim.hpp"
+
+#include "Core/Event.hpp"
+#include "Services/Log.hpp"
+#include "Sim/Octree.hpp"
+
+#include <string>
+
+static_assert(sizeof(Particle) == NB_PARTICLE_STRIDE, "Particle layout differs from the one the engine was built for");
+static_assert(offsetof(Particle, Velocity) == NB_OFF_VELOCITY && offsetof(Particle, Forces) == NB_OFF_FORCES &&
+              offsetof(Particle, Mass) == NB_OFF_MASS, "Particle layout differs from the one the engine was built for");
+
+B200Sim::B200Sim(ID3D11DeviceContext*, EMode mode, int device) : Mode(mode)
+{
+    LOGM(mode == EMode::AllPairs ? "Brute Force B200" : "Barnes-Hut B200")
+
+    nb_config cfg;
+    nb_default_config(&cfg);
+    cfg.device = device;
+    cfg.mode = (mode == EMode::AllPairs) ? NB_MODE_ALLPAIRS : NB_MODE_BARNESHUT;
+    cfg.theta = static_cast<float>(Octree::Theta);          // process-global in the reference (Octree.cpp:5)
+    if (nb_create(&cfg, &Handle) != NB_OK)
+    {
+        LOGE(std::string("B200 engine unavailable: ") + nb_last_error())
+        Handle = nullptr;                                    // Update() becomes a logged no-op, like
+        return;                                              // BruteForceGPU without its shader (:25-33)
+    }
+
+    if (mode == EMode::BarnesHut)
+    {
+        EventStream::Register(EEvent::BHThetaChanged, [this](const EventData& data) {
+            SetTheta(EventValue<FloatEventData>(data));
+        });
+    }
+}
+
+B200Sim::~B200Sim()
+{
+    Shutdown();
+}
+
+void B200Sim::Shutdown()
+{
+    Unpin();
+    if (Handle)
+    {
+        nb_destroy(Handle);
+        Handle = nullptr;
+    }
+}
+
+void B200Sim::SetTheta(float theta)
+{
+    if (Handle && nb_set_theta(Handle, theta) != NB_OK)
+        LOGE(std::string("B200Sim::SetTheta: ") + nb_last_error())
+}
+
+void B200Sim::Pin()
+{
+    Unpin();
+    if (!Particles || Particles->empty()) return;
+    // Page-lock the caller's array so the per-Update upload / write-back run at full PCIe rate.
+    if (nb_host_register(Particles->data(), Particles->size() * sizeof(Particle)) == NB_OK)
+    {
+        Pinned = Particles->data();
+        PinnedBytes = Particles->size() * sizeof(Particle);
+    }
+}
+
+void B200Sim::Unpin()
+{
+    if (Pinned) nb_host_unregister(Pinned);
+    Pinned = nullptr;
+    PinnedBytes = 0;
+}
+
+void B200Sim::Init(std::vector<Particle>& particles)
+{
+    Particles = &particles;
+    if (!Handle || particles.empty()) return;
+    Pin();
+    if (nb_init_aos(Handle, particles.data(), particles.size(), sizeof(Particle)) != NB_OK)
+        LOGE(std::string("B200Sim::Init: ") + nb_last_error())
+}
+
+void B200Sim::Update(float dt)
+{
+    if (!Handle || !Particles || Particles->empty()) return;
+    // the vector may have been reallocated by the caller since Init (resize + re-Init is the
+    // reference's protocol, SimulationState.cpp:218-227, but stay safe if it was not followed)
+    if (Pinned != Particles->data() || PinnedBytes != Particles->size() * sizeof(Particle)) Pin();
+    if (nb_update_aos(Handle, Particles->data(), Particles->size(), sizeof(Particle), dt) != NB_OK)
+        LOGE(std::string("B200Sim::Update: ") + nb_last_error())
+}
+
+std::unique_ptr<INBodySim> CreateB200NBodySim(ID3D11DeviceContext* context, ENBodySim type)
+{
+    switch (type)
+    {
+        case ENBodySim::BruteForceGPU:
+            return std::make_unique<B200Sim>(context, B200Sim::EMode::AllPairs);
+        case ENBodySim::BarnesHut:
+            return std::make_unique<B200Sim>(context, B200Sim::EMode::BarnesHut);
+        default:
+            return CreateNBodySim(context, type);
+    }
+}
