@@ -54,6 +54,10 @@ struct TreeBuffers
     float4* walk_a = nullptr;       // [2n-1] {com.x, com.y, com.z, G*M}
     int4* walk_b = nullptr;         // [2n-1] {open threshold (float bits), first slot, next-if-open, next-if-skip}
     unsigned long long* stats = nullptr;   // [3] accepted cells, pair evals, node visits
+    unsigned int* cnt = nullptr;    // [n+1] owning nodes per first slot
+    unsigned int* pref = nullptr;   // [n+1] exclusive scan of cnt
+    int* rank = nullptr;            // [2n]  pre-order rank of every traversal record
+    unsigned int* tlist = nullptr;  // [n]   owned targets in Morton order (world > 1)
     int sort_bits_done = 0;
     int cur = 0;                    // which ping-pong half holds the sorted result
     size_t n_inbounds_host = 0;

@@ -35,10 +35,9 @@ namespace nb
 constexpr int kLevels = 21;
 constexpr unsigned long long kOutside = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kEnd = -1;
-constexpr int kNone = -2;
 
 // counters[] slots
-enum { C_INBOUNDS = 0, C_START = 1, C_WORDS = 8 };
+enum { C_INBOUNDS = 0, C_TOTAL = 1, C_WORDS = 8 };
 
 // ------------------------------------------------------------------------------------------------
 // K3: Morton codes.  Same comparison descent as the CPU restatement (oracle/nbody_port.c,
@@ -241,7 +240,7 @@ __device__ __forceinline__ int delta_fn(const unsigned long long* __restrict__ k
 __global__ void __launch_bounds__(256)
 k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ counters, int leaf_base,
          int* __restrict__ child_l, int* __restrict__ child_r, int* __restrict__ prefix, int* __restrict__ parent,
-         unsigned int* __restrict__ flags)
+         unsigned int* __restrict__ flags, int* __restrict__ first_slot)
 {
     const int m = (int)counters[C_INBOUNDS];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,6 +267,7 @@ k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __rest
     child_l[i] = cl;
     child_r[i] = cr;
     prefix[i] = dnode;
+    first_slot[i] = lo;
     parent[cl] = i;
     parent[cr] = i;
     flags[i] = 0;
@@ -341,13 +341,81 @@ __device__ __forceinline__ bool owns_cell(int id, const int* __restrict__ prefix
     return level_of(prefix[id]) > level_of(prefix[p]);
 }
 
-__device__ __forceinline__ int enter_subtree(int id, int leaf_base, const int* __restrict__ child_l,
-                                             const int* __restrict__ prefix, const int* __restrict__ parent)
+// K6b: depth-first (pre-order) layout of the nodes the traversal can visit -- leaves and the
+// radix-tree nodes that own an octree cell.  Opening a node then means "next record" and skipping
+// a subtree is a forward jump, so a walk reads memory front to back (L1-friendly).
+// rank(v) = #records before v in pre-order:
+//   every leaf slot < first(v) precedes v; an owning node u precedes v iff first(u) < first(v), or
+//   first(u) == first(v) and u is a proper ancestor of v (same first <=> chain of left children).
+// With cnt[f] = #owning nodes whose range starts at slot f and P = exclusive scan of cnt:
+//   rank(node v) = first(v) + P[first(v)] + #owning proper ancestors with the same first
+//   rank(leaf j) = j + P[j + 1]
+__global__ void __launch_bounds__(256)
+k_count_owned(const unsigned int* __restrict__ counters, const int* __restrict__ prefix, const int* __restrict__ parent,
+              const int* __restrict__ first_slot, unsigned int* __restrict__ cnt)
 {
-    while (id < leaf_base && !owns_cell(id, prefix, parent)) id = child_l[id];
-    return id;
+    const int m = (int)counters[C_INBOUNDS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m - 1 && owns_cell(i, prefix, parent)) atomicAdd(&cnt[first_slot[i]], 1u);
 }
 
+__global__ void __launch_bounds__(256)
+k_scan_apply(const unsigned int* __restrict__ in, int n, const unsigned int* __restrict__ block_prefix,
+             unsigned int* __restrict__ out)
+{
+    __shared__ unsigned int warp_sums[8];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = block_prefix[blockIdx.x];
+    __syncthreads();
+    const int base = blockIdx.x * 4096;
+    for (int k = 0; k < 16; ++k)
+    {
+        const int i = base + k * 256 + threadIdx.x;
+        const unsigned int v = i < n ? in[i] : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned int wprefix = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += warp_sums[w];
+        const unsigned int c = carry;
+        if (i < n) out[i] = c + wprefix + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c + wprefix + x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int* __restrict__ child_l,
+       const int* __restrict__ prefix, const int* __restrict__ parent, const int* __restrict__ first_slot,
+       const unsigned int* __restrict__ pref, int* __restrict__ rank)
+{
+    const int m = (int)counters[C_INBOUNDS];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) counters[C_TOTAL] = (unsigned int)m + pref[n];
+    if (t < m) rank[leaf_base + t] = t + (int)pref[t + 1];
+    if (t < m - 1 && owns_cell(t, prefix, parent))
+    {
+        int above = 0, v = t;
+        for (;;)
+        {
+            const int p = parent[v];
+            if (p == kEnd || child_l[p] != v) break;
+            if (owns_cell(p, prefix, parent)) ++above;
+            v = p;
+        }
+        const int f = first_slot[t];
+        rank[t] = f + (int)pref[f] + above;
+    }
+}
+
+// The record after the subtree of `id` in pre-order (kEnd if none).
 __device__ __forceinline__ int after_subtree(int id, int leaf_base, const int* __restrict__ child_l,
                                              const int* __restrict__ child_r, const int* __restrict__ prefix,
                                              const int* __restrict__ parent)
@@ -356,43 +424,49 @@ __device__ __forceinline__ int after_subtree(int id, int leaf_base, const int* _
     {
         const int p = parent[id];
         if (p == kEnd) return kEnd;
-        if (child_l[p] == id) return enter_subtree(child_r[p], leaf_base, child_l, prefix, parent);
+        if (child_l[p] == id)
+        {
+            int r = child_r[p];
+            while (r < leaf_base && !owns_cell(r, prefix, parent)) r = child_l[r];
+            return r;
+        }
         id = p;
     }
 }
 
+// Traversal records, 32 bytes each, at their pre-order rank: {com.xyz, G M 2^-27} and
+// {open threshold, rank of the record after this subtree, body, 0}.  Threshold: leaves -1 (always
+// evaluated), owning nodes (width / theta)^2.
 __global__ void __launch_bounds__(256)
-k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ order, unsigned int* __restrict__ counters,
+k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ counters,
            int leaf_base, const int* __restrict__ child_l, const int* __restrict__ child_r,
            const int* __restrict__ prefix, const int* __restrict__ parent, const double* __restrict__ nw,
            const double* __restrict__ ns, size_t plane, float root_width, float inv_theta,
-           float4* __restrict__ walk_a, int4* __restrict__ walk_b)
+           const int* __restrict__ rank, float4* __restrict__ nodes)
 {
     const int m = (int)counters[C_INBOUNDS];
+    const int total = (int)counters[C_TOTAL];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) counters[C_START] = (unsigned int)(m >= 2 ? 0 : (m == 1 ? leaf_base : kEnd));
     if (t < m)
     {
-        // leaf slot t
-        const int id = leaf_base + t;
+        const int r = rank[leaf_base + t];
         const unsigned int body = order[t];
         const float4 p = posw[body];
-        const int nxt = m >= 2 ? after_subtree(id, leaf_base, child_l, child_r, prefix, parent) : kEnd;
-        walk_a[id] = make_float4(p.x, p.y, p.z, p.w * kPreScale);
-        walk_b[id] = make_int4(__float_as_int(-1.0f), nxt, nxt, (int)body);
+        nodes[2 * (size_t)r] = make_float4(p.x, p.y, p.z, p.w * kPreScale);
+        nodes[2 * (size_t)r + 1] = make_float4(-1.0f, __int_as_float(r + 1), __int_as_float((int)body), 0.f);
     }
-    if (t < m - 1)
+    if (t < m - 1 && owns_cell(t, prefix, parent))
     {
-        const int id = t;
-        if (!owns_cell(id, prefix, parent)) return;   // never visited
-        const double w = nw[id];
+        const int r = rank[t];
+        const int nxt = after_subtree(t, leaf_base, child_l, child_r, prefix, parent);
+        const int skip = nxt == kEnd ? total : rank[nxt];
+        const double w = nw[t];
         const double inv = w != 0.0 ? 1.0 / w : 0.0;
-        const float width = ldexpf(root_width, -level_of(prefix[id]));
+        const float width = ldexpf(root_width, -level_of(prefix[t]));
         const float lim = width * inv_theta;
-        walk_a[id] = make_float4((float)(ns[id] * inv), (float)(ns[plane + id] * inv), (float)(ns[2 * plane + id] * inv),
-                                 (float)w * kPreScale);
-        walk_b[id] = make_int4(__float_as_int(lim * lim), enter_subtree(child_l[id], leaf_base, child_l, prefix, parent),
-                               after_subtree(id, leaf_base, child_l, child_r, prefix, parent), -1);
+        nodes[2 * (size_t)r] = make_float4((float)(ns[t] * inv), (float)(ns[plane + t] * inv), (float)(ns[2 * plane + t] * inv),
+                                           (float)w * kPreScale);
+        nodes[2 * (size_t)r + 1] = make_float4(lim * lim, __int_as_float(skip), __int_as_float(-1), 0.f);
     }
 }
 
@@ -401,16 +475,15 @@ k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ ord
 // sorted list and walks the union of what its lanes need; node records are warp-uniform loads.
 // Every lane applies its OWN acceptance test (the reference's per-particle decisions, not a
 // group criterion): a lane that accepts a cell the warp still has to open for another lane parks
-// until the walk leaves that subtree (the walk reaches `next-if-skipped` of the accepted node).
+// until the walk has left that subtree (cur >= the record after it).
 // Interaction: same law as all-pairs, a += G M (c - p) / (|d| (d^2 + S)); the self term and
 // coincident bodies vanish through the epsilon (see allpairs.cuh).
 // ------------------------------------------------------------------------------------------------
 template <bool STATS>
 __global__ void __launch_bounds__(256)
 k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ tlist,
-       int ntargets, const unsigned int* __restrict__ counters, const float4* __restrict__ walk_a,
-       const int4* __restrict__ walk_b, int first, int count, float sc, double* __restrict__ acc,
-       unsigned long long* __restrict__ stats)
+       int ntargets, const unsigned int* __restrict__ counters, const float4* __restrict__ nodes,
+       int first, int count, float sc, double* __restrict__ acc, unsigned long long* __restrict__ stats)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < ntargets;
@@ -421,21 +494,22 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
         body = order[tlist ? tlist[t] : (unsigned int)t];
         p = posw[body];
     }
-    int cur = (int)counters[C_START];
-    int parked = kNone;
+    const int total = (int)counters[C_TOTAL];
+    int cur = 0;
+    int parked = 0;                      // the lane is idle while cur < parked
     float ax = 0.f, ay = 0.f, az = 0.f;
     unsigned int n_cells = 0, n_leaves = 0, n_visits = 0;
-    while (cur != kEnd)
+    while (cur < total)
     {
-        const float4 a = walk_a[cur];
-        const int4 b = walk_b[cur];
-        if (parked == cur) parked = kNone;
-        const bool active = valid && parked == kNone;
+        const float4 a = nodes[2 * (size_t)cur];
+        const float4 b = nodes[2 * (size_t)cur + 1];
+        const bool active = valid && cur >= parked;
         const float dx = a.x - p.x, dy = a.y - p.y, dz = a.z - p.z;
         float d2 = dx * dx;
         d2 = fmaf(dy, dy, d2);
         d2 = fmaf(dz, dz, d2);
-        const float thr = __int_as_float(b.x);
+        const float thr = b.x;
+        const int skip = __float_as_int(b.y);
         const bool accept = d2 > thr;
         const bool use = active && accept;
         const float tt = fmaf(d2, kPreScale, sc);
@@ -445,14 +519,14 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
         ax = fmaf(s, dx, ax);
         ay = fmaf(s, dy, ay);
         az = fmaf(s, dz, az);
-        if (use) parked = b.z;
+        if (use) parked = skip;
         if (STATS && active)
         {
             ++n_visits;
-            if (accept) { if (thr < 0.f) n_leaves += ((unsigned int)b.w != body); else ++n_cells; }
+            if (accept) { if (thr < 0.f) n_leaves += ((unsigned int)__float_as_int(b.z) != body); else ++n_cells; }
         }
         const bool open = __any_sync(0xffffffffu, active && !accept);
-        cur = open ? b.y : b.z;
+        cur = open ? cur + 1 : skip;
     }
     if (valid)
     {
@@ -555,7 +629,7 @@ void tree_release(nb_sim* h)
     for (int k = 0; k < 2; ++k) { cudaFree(t.keys[k]); cudaFree(t.vals[k]); t.keys[k] = nullptr; t.vals[k] = nullptr; }
     cudaFree(t.hist); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
     cudaFree(t.range); cudaFree(t.flags); cudaFree(t.nmass); cudaFree(t.ncom); cudaFree(t.walk_a);
-    cudaFree(t.walk_b); cudaFree(t.stats);
+    cudaFree(t.walk_b); cudaFree(t.stats); cudaFree(t.cnt); cudaFree(t.pref); cudaFree(t.rank); cudaFree(t.tlist);
     t = TreeBuffers();
 }
 
@@ -577,12 +651,15 @@ int tree_reserve(nb_sim* h)
     NB_CUDA(cudaMalloc(&t.child, 2 * n * sizeof(int)));
     NB_CUDA(cudaMalloc(&t.parent, 2 * n * sizeof(int)));
     NB_CUDA(cudaMalloc(&t.prefix, n * sizeof(int)));
-    NB_CUDA(cudaMalloc(&t.range, n * sizeof(unsigned int)));          // target-selection flags / list
+    NB_CUDA(cudaMalloc(&t.range, n * sizeof(int)));                   // first slot of every node's range
+    NB_CUDA(cudaMalloc(&t.cnt, (n + 1) * sizeof(unsigned int)));
+    NB_CUDA(cudaMalloc(&t.pref, (n + 1) * sizeof(unsigned int)));
+    NB_CUDA(cudaMalloc(&t.rank, 2 * n * sizeof(int)));
+    NB_CUDA(cudaMalloc(&t.tlist, n * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.flags, n * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.nmass, n * sizeof(double)));
     NB_CUDA(cudaMalloc(&t.ncom, 3 * n * sizeof(double)));
-    NB_CUDA(cudaMalloc(&t.walk_a, 2 * n * sizeof(float4)));
-    NB_CUDA(cudaMalloc(&t.walk_b, 2 * n * sizeof(int4)));
+    NB_CUDA(cudaMalloc(&t.walk_a, 4 * n * sizeof(float4)));           // 2n records x 32 B
     NB_CUDA(cudaMalloc(&t.stats, 3 * sizeof(unsigned long long)));
     NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), h->stream));
     t.capacity = n;
@@ -620,12 +697,27 @@ int tree_build(nb_sim* h)
     const int leaf_base = n;
     int* child_l = t.child;
     int* child_r = t.child + n;
-    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, child_l, child_r, t.prefix, t.parent, t.flags);
+    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, child_l, child_r, t.prefix, t.parent, t.flags,
+                                                t.range);
     k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, child_l, child_r, t.parent,
                                                    t.flags, t.nmass, t.ncom, (size_t)n);
+    // pre-order ranks: count owning nodes per first slot, exclusive scan, rank, then the records
+    {
+        const int words = n + 1;
+        const int sblocks = (words + 4095) / 4096;
+        unsigned int* sums = t.hist;                 // radix-sort scratch is free again
+        unsigned int* total = t.hist + sblocks;
+        NB_CUDA(cudaMemsetAsync(t.cnt, 0, (size_t)words * sizeof(unsigned int), st));
+        k_count_owned<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, t.prefix, t.parent, t.range, t.cnt);
+        k_block_sums<<<sblocks, 256, 0, st>>>(t.cnt, words, sums);
+        k_rs_scan_rows<<<1, 256, 0, st>>>(sums, sblocks, total);
+        k_scan_apply<<<sblocks, 256, 0, st>>>(t.cnt, words, sums, t.pref);
+        k_rank<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, n, leaf_base, child_l, t.prefix, t.parent, t.range, t.pref, t.rank);
+        h->last_launches += 5;
+    }
     k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, child_l, child_r, t.prefix,
                                                   t.parent, t.nmass, t.ncom, (size_t)n, 2.0f * h->cfg.bounds,
-                                                  1.0f / h->cfg.theta, t.walk_a, t.walk_b);
+                                                  1.0f / h->cfg.theta, t.rank, t.walk_a);
     h->last_launches += 3;
     NB_CUDA(cudaGetLastError());
     t.built = true;
@@ -652,21 +744,21 @@ int tree_walk(nb_sim* h)
         k_select_flags<<<blocks_for(n, 256), 256, 0, st>>>(order, n, (int)h->first, (int)h->count, flag);
         k_block_sums<<<blocks, 256, 0, st>>>(flag, n, sums);
         k_rs_scan_rows<<<1, 256, 0, st>>>(sums, blocks, total);
-        k_compact<<<blocks, 256, 0, st>>>(flag, n, sums, reinterpret_cast<unsigned int*>(t.range));
+        k_compact<<<blocks, 256, 0, st>>>(flag, n, sums, t.tlist);
         h->last_launches += 4;
-        tlist = reinterpret_cast<const unsigned int*>(t.range);
+        tlist = t.tlist;
         ntargets = (int)h->count;
     }
     const float sc = (float)(h->cfg.softening * (double)kPreScale);
     if (g_walk_stats)
     {
         NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), st));
-        k_walk<true><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, t.walk_b,
+        k_walk<true><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a,
                                                               (int)h->first, (int)h->count, sc, h->acc, t.stats);
     }
     else
     {
-        k_walk<false><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, t.walk_b,
+        k_walk<false><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a,
                                                                (int)h->first, (int)h->count, sc, h->acc, t.stats);
     }
     ++h->last_launches;
