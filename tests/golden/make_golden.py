@@ -51,6 +51,32 @@ def main():
                         max_depth=stats["max_depth"], nodes=stats["nodes"],
                         work=np.array([work["cell_evals"], work["leaf_evals"], work["visits"]]),
                         state5=q.view(np.uint8).reshape(1024, 104), dt=np.float32(0.02 / 60))
+    # 5. energy drift of the reference Barnes-Hut path on the two-galaxy collision scene (config 5 at
+    #    a CPU-feasible size): N = 4096, seeds 42/43, separation 2000, approach 2e16, theta 0.5,
+    #    dt = 0.02/60, 1000 steps; E = sum 1/2 m v^2 + Scale * sum U(r) evaluated exactly (all pairs).
+    from oracle import port
+    n = 4096
+    a = ref.seed(n // 2, ref.SEED_GALAXY, 42, 1.0)
+    b = ref.seed(n // 2, ref.SEED_GALAXY, 43, 1.0)
+    p = np.concatenate([a, b]).astype(ref.PARTICLE_DTYPE)
+    scene = np.zeros(n, dtype=ref.PARTICLE_DTYPE)
+    for name in scene.dtype.names:
+        scene[name] = np.concatenate([a[name], b[name]])
+    sign = np.where(np.arange(n) < n // 2, -1.0, 1.0)
+    scene["Position"][:, 0] += (sign * 0.5 * 2000.0).astype(np.float32)
+    scene["Velocity"][:, 0] -= sign * 2e16
+    dt = np.float32(0.02 / 60)
+    energies = [port.energy(scene)]
+    q = scene
+    for _ in range(10):
+        q, _, _ = ref.barneshut_run(q, dt, 100, 0.5, workers=4)
+        energies.append(port.energy(q))
+    e = np.array(energies)
+    tot = e.sum(axis=1)
+    drift = np.abs(tot - tot[0]) / abs(tot[0])
+    print("reference BH energy drift per 100 steps:", drift)
+    np.savez_compressed(os.path.join(HERE, "energy_drift_n4096.npz"), scene=scene.view(np.uint8).reshape(n, 104),
+                        energies=e, drift=drift, dt=dt, theta=0.5, separation=2000.0, approach=2e16)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -261,3 +261,34 @@ def test_large_n_sampled_parity(pkg):
     assert np.all(codes[1:] >= codes[:-1])
     assert np.array_equal(np.sort(order), np.arange(len(order)))
     sim.close()
+
+
+def test_energy_drift_within_twice_the_reference(pkg):
+    """BASELINE.json north_star: energy drift over 1000 steps within 2x the reference's.  Two-galaxy
+    collision scene (config 5) at the size the reference's CPU path finishes in seconds; the
+    reference's drift (tests/golden/energy_drift_n4096.npz, from oracle/_ref) and ours use the same
+    estimator: E = sum 1/2 m v^2 + Scale * sum_{i<j} U(r), all pairs, fp64."""
+    g = load_golden("energy_drift_n4096.npz")
+    scene = as_particles(g["scene"], pkg.PARTICLE_DTYPE).copy()
+    n = len(scene)
+    mine = pkg.seed_collision_host(n, 42, 1.0, separation=float(g["separation"]), approach_speed=float(g["approach"]))
+    for f in ("Position", "Velocity", "Mass"):
+        assert np.array_equal(mine[f], scene[f])               # the product seeder builds the same scene
+    sim = bh(pkg, theta=float(g["theta"]))
+    sim.init(scene)
+    ke0, pe0 = sim.energy()
+    assert abs(ke0 - g["energies"][0, 0]) < 1e-9 * abs(ke0) and abs(pe0 - g["energies"][0, 1]) < 1e-6 * abs(pe0)
+    e0 = ke0 + pe0
+    drift = [0.0]
+    for _ in range(10):
+        sim.step(float(g["dt"]), 100)
+        ke, pe = sim.energy()
+        drift.append(abs(ke + pe - e0) / abs(e0))
+    drift = np.array(drift)
+    print("energy drift ours     :", drift)
+    print("energy drift reference:", g["drift"])
+    assert drift[-1] <= 2.0 * g["drift"][-1]
+    assert drift.max() <= 2.0 * g["drift"].max()
+    # and the trajectories are the reference's: the two drifts track each other
+    assert np.all(np.abs(drift[1:] - g["drift"][1:]) <= 0.25 * g["drift"][1:] + 1e-6)
+    sim.close()
