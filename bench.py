@@ -193,6 +193,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="all-pairs kernel table index")
     ap.add_argument("--splits", type=int, default=0)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: fused kick-drift + peer-memory stores (p2p) or kick-drift + ncclAllGather (nccl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -232,7 +234,10 @@ def main():
     sim.init(particles)
     if world > 1:
         multi = importlib.import_module("procedural-universe_b200.multi")
-        multi.connect(sim, rank)           # library-owned NCCL communicator; id travels over torch.distributed
+        if args.exchange == "p2p":
+            multi.connect_p2p(sim, rank, world)   # CUDA IPC handles travel over torch.distributed
+        else:
+            multi.connect(sim, rank)           # library-owned NCCL communicator; id travels over torch.distributed
     first, count = sim.owned_range()
 
     # parity spot check against the oracle (untimed): a few owned targets x all N sources
@@ -327,7 +332,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if wl["mode"] == "allpairs" else "f32 (f64 velocities / centre-of-mass)",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "bodies": n, "dt": dt, "parallelism": f"target-sharded x{world}",
+            "config": {"workload": wl["desc"], "name": args.workload, "bodies": n, "dt": dt, "parallelism": f"target-sharded x{world}" + (f", exchange={args.exchange}" if world > 1 else ""),
                        "l2": "256 MiB memset between timed steps (inside the timed region); sources (16 B/body) are re-read from L2 by design",
                        "kernel_variant": args.variant},
             "gpu_launches": launches,

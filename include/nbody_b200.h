@@ -184,6 +184,17 @@ NB_API int nb_comm_init(nb_handle h, const uint8_t id[128]);
 /* Raw device pointers for hosts that prefer to run the exchange themselves (e.g. through
  * torch.distributed.all_gather_into_tensor): the float4 array of all n bodies. */
 NB_API int nb_device_posw(nb_handle h, void** dev_ptr, size_t* bytes);
+/* Fused exchange over NVLink peer memory (one process per GPU, one box): after nb_init_*, every rank
+ * exports NB_P2P_HANDLE_BYTES opaque bytes (CUDA IPC handles of its two position buffers and its
+ * flag array), the launcher all-gathers them in rank order, every rank attaches.  From then on the
+ * kick-drift kernel stores each new position directly into every rank's position array and no
+ * collective is launched (csrc/p2p.cu); takes precedence over nb_comm_init. */
+#define NB_MAX_PEERS 16
+#define NB_P2P_HANDLE_BYTES 192
+NB_API int nb_p2p_export(nb_handle h, uint8_t handles[NB_P2P_HANDLE_BYTES]);
+NB_API int nb_p2p_attach(nb_handle h, const uint8_t* all_handles /* world x NB_P2P_HANDLE_BYTES */);
+/* Same for handles that live in ONE process (peers[r] = the handle of rank r). */
+NB_API int nb_p2p_attach_local(nb_handle h, const nb_handle* peers);
 /* Tells the handle that the host exchanged positions itself after the last step. */
 NB_API int nb_mark_exchanged(nb_handle h);
 

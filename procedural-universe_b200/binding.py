@@ -90,6 +90,9 @@ def load():
     L.nb_comm_init.argtypes = [vp, vp]
     L.nb_device_posw.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.nb_mark_exchanged.argtypes = [vp]
+    L.nb_p2p_export.argtypes = [vp, vp]
+    L.nb_p2p_attach.argtypes = [vp, vp]
+    L.nb_p2p_attach_local.argtypes = [vp, C.POINTER(vp)]
     L.nb_last_step_timing.argtypes = [vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int)]
     L.nb_probe_fp32_peak.argtypes = [vp, C.POINTER(f64)]
     L.nb_last_build_timing.argtypes = [vp, C.POINTER(f32)]
@@ -264,6 +267,22 @@ class Sim:
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         _check(self._L.nb_device_posw(self._h, C.byref(ptr), C.byref(nbytes)))
         return _CudaArray(ptr.value, nbytes.value, self)
+
+    P2P_HANDLE_BYTES = 192
+
+    def p2p_export(self):
+        buf = (C.c_uint8 * self.P2P_HANDLE_BYTES)()
+        _check(self._L.nb_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, all_handles):
+        blob = b"".join(all_handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(self._L.nb_p2p_attach(self._h, buf))
+
+    def p2p_attach_local(self, sims):
+        arr = (C.c_void_p * len(sims))(*[s._h for s in sims])
+        _check(self._L.nb_p2p_attach_local(self._h, arr))
 
     def mark_exchanged(self):
         _check(self._L.nb_mark_exchanged(self._h))

@@ -22,7 +22,10 @@ void set_error(const char* fmt, ...)
 
 static int free_state(nb_sim* h)
 {
-    cudaFree(h->posw); h->posw = nullptr;
+    p2p_release(h);
+    cudaFree(h->posw_buf[0]); cudaFree(h->posw_buf[1]);
+    h->posw_buf[0] = h->posw_buf[1] = nullptr; h->posw = nullptr; h->posw_cur = 0;
+    cudaFree(h->p2p_flags); h->p2p_flags = nullptr;
     cudaFree(h->vel); h->vel = nullptr;
     cudaFree(h->mass); h->mass = nullptr;
     cudaFree(h->acc); h->acc = nullptr;
@@ -148,7 +151,9 @@ static int set_bodies(nb_sim* h, size_t n)
         h->first = rank * n / world;
         h->count = (rank + 1) * n / world - h->first;
         NB_REQUIRE(h->count > 0, NB_ERR_ARG, "fewer bodies than ranks");
-        NB_CUDA(cudaMalloc(&h->posw, n * sizeof(float4)));
+        NB_CUDA(cudaMalloc(&h->posw_buf[0], n * sizeof(float4)));
+        h->posw = h->posw_buf[0];
+        h->posw_cur = 0;
         NB_CUDA(cudaMalloc(&h->vel, 3 * h->count * sizeof(double)));
         NB_CUDA(cudaMalloc(&h->mass, h->count * sizeof(double)));
         NB_CUDA(cudaMalloc(&h->acc, 3 * h->count * sizeof(double)));
@@ -335,14 +340,22 @@ int nb_step(nb_handle h, float dt, int nsteps)
         NB_REQUIRE(h->exchanged, NB_ERR_STATE,
                    "world > 1 without nb_comm_init: call nb_mark_exchanged after exchanging positions");
         const bool last = (s == nsteps - 1);
+        if (h->p2p_attached) NB_CHECK(p2p_wait(h));          // every peer's positions of the last step are in
         NB_CHECK(compute_forces(h, last));
-        NB_CHECK(launch_kick_drift(h, dt));
         h->acc_valid = false;
         h->forces_from_last_step = true;
-        if (h->cfg.world > 1)
+        if (h->p2p_attached)
         {
-            if (h->nccl_comm != nullptr) NB_CHECK(comm_allgather_posw(h));
-            else h->exchanged = false;
+            NB_CHECK(p2p_kick_drift_push(h, dt));            // ONE kernel: integrate + store into every rank
+        }
+        else
+        {
+            NB_CHECK(launch_kick_drift(h, dt));
+            if (h->cfg.world > 1)
+            {
+                if (h->nccl_comm != nullptr) NB_CHECK(comm_allgather_posw(h));
+                else h->exchanged = false;
+            }
         }
     }
     NB_CUDA(cudaEventRecord(h->ev[1], h->stream));
@@ -493,6 +506,7 @@ int nb_compute_accel(nb_handle h)
     NB_CUDA(cudaSetDevice(h->cfg.device));
     h->last_launches = 0;
     h->timing_valid = false;
+    if (h->p2p_attached) NB_CHECK(p2p_wait(h));
     NB_CUDA(cudaEventRecord(h->ev[0], h->stream));
     NB_CHECK(compute_forces(h, true));
     if (h->cfg.mode == NB_MODE_ALLPAIRS) NB_CHECK(launch_reduce_partials(h));

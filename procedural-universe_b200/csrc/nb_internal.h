@@ -77,7 +77,9 @@ struct nb_sim
     size_t first = 0;      // owned (target) range
     size_t count = 0;
 
-    float4* posw = nullptr;      // [n]        {x, y, z, (float)(G*m)}
+    float4* posw = nullptr;      // [n]        {x, y, z, (float)(G*m)}  == posw_buf[posw_cur]
+    float4* posw_buf[2] = {nullptr, nullptr};   // second buffer only with the fused P2P exchange
+    int posw_cur = 0;
     double* vel = nullptr;       // [3][count] velocity planes of owned bodies
     double* mass = nullptr;      // [count]
     double* acc = nullptr;       // [3][count] accelerations of the last force evaluation
@@ -102,6 +104,14 @@ struct nb_sim
     nb::TreeBuffers tree;
 
     void* nccl_comm = nullptr;   // ncclComm_t
+
+    // fused kick-drift + exchange over peer memory (p2p.cu)
+    bool p2p_attached = false;
+    bool p2p_ipc = false;
+    unsigned int p2p_step = 0;
+    unsigned int* p2p_flags = nullptr;            // [NB_MAX_PEERS] step counters raised by the peers
+    void* peer_posw[2][NB_MAX_PEERS] = {};
+    void* peer_flags[NB_MAX_PEERS] = {};
 };
 
 namespace nb
@@ -125,6 +135,12 @@ int comm_unique_id(uint8_t id[128]);
 int comm_init(nb_sim* h, const uint8_t id[128]);
 int comm_allgather_posw(nb_sim* h);
 void comm_destroy(nb_sim* h);
+
+// p2p.cu
+int p2p_prepare(nb_sim* h);
+int p2p_wait(nb_sim* h);
+int p2p_kick_drift_push(nb_sim* h, float dt);
+void p2p_release(nb_sim* h);
 
 // seed_host.cpp / seed_device.cu
 int seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale);

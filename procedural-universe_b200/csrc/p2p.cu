@@ -1,0 +1,253 @@
+// Fused kick-drift + position exchange over NVLink peer memory.
+//
+// The baseline exchange is "kick-drift kernel, then ncclAllGather" (nccl_dl.cpp).  This variant is
+// ONE kernel for both: every thread integrates its body and stores the new float4 {x, y, z, G m}
+// straight into the position array of EVERY rank (its own and P-1 peer-mapped ones), so the bytes
+// cross NVLink / NVSwitch while the rest of the grid is still integrating, and no separate
+// collective is launched.  What remains of the collective is its synchronisation: a per-step flag
+// each rank raises on all peers once its stores are out (release, system scope) and a one-block
+// wait at the head of the next force pass (acquire).
+//
+// Positions are double-buffered: step s reads buffer s&1 and writes buffer (s+1)&1 everywhere.  A
+// rank can only reach the kick-drift of step s+1 (which overwrites buffer s&1 on its peers) after
+// every peer has raised flag s+1, i.e. after every peer has finished its own step-s force pass over
+// buffer s&1 -- so no rank ever writes into a buffer a peer is still reading.
+//
+// Peers are attached either through CUDA IPC handles (one process per GPU; the 192 bytes per rank
+// travel over the launcher's torch.distributed / MPI) or, for handles living in one process, by
+// handle (nb_p2p_attach_local; used by the single-GPU test).
+#include <cstring>
+
+#include "nb_internal.h"
+
+namespace nb
+{
+
+struct PeerTable
+{
+    float4* posw[2][NB_MAX_PEERS];
+    unsigned int* flags[NB_MAX_PEERS];
+    int world, rank;
+};
+
+__global__ void __launch_bounds__(256)
+k_kick_drift_push(PeerTable pt, int cur, int first, int count, double* __restrict__ vel,
+                  const double* __restrict__ acc_part, int splits, double* __restrict__ acc, double dt,
+                  double pos_scale)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const size_t plane = (size_t)count;
+    double ax, ay, az;
+    if (acc_part != nullptr)
+    {
+        ax = ay = az = 0.0;
+        for (int s = 0; s < splits; ++s)
+        {
+            const double* p = acc_part + (size_t)s * 3 * plane;
+            ax += p[i]; ay += p[plane + i]; az += p[2 * plane + i];
+        }
+        acc[i] = ax; acc[plane + i] = ay; acc[2 * plane + i] = az;
+    }
+    else
+    {
+        ax = acc[i]; ay = acc[plane + i]; az = acc[2 * plane + i];
+    }
+    double vx = vel[i], vy = vel[plane + i], vz = vel[2 * plane + i];
+    vx += ax * dt; vy += ay * dt; vz += az * dt;
+    vel[i] = vx; vel[plane + i] = vy; vel[2 * plane + i] = vz;
+    float4 p = pt.posw[cur][pt.rank][first + i];
+    p.x += (float)((vx * dt) / pos_scale);
+    p.y += (float)((vy * dt) / pos_scale);
+    p.z += (float)((vz * dt) / pos_scale);
+    const int nxt = cur ^ 1;
+#pragma unroll 1
+    for (int r = 0; r < pt.world; ++r)
+    {
+        // start with the own copy, then walk the peers round-robin so the ranks do not all hammer
+        // the same destination GPU at the same time
+        const int dst = (pt.rank + r) % pt.world;
+        pt.posw[nxt][dst][first + i] = p;
+    }
+}
+
+// Raised after the push kernel has completed (stream order): my stores of `step` are out.
+__global__ void k_signal(PeerTable pt, unsigned int step)
+{
+    const int r = threadIdx.x;
+    if (r < pt.world)
+    {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[r] + pt.rank), "r"(step) : "memory");
+    }
+}
+
+// Head of the next force pass: every peer has pushed its positions of `step`.
+__global__ void k_wait(const unsigned int* my_flags, int world, unsigned int step)
+{
+    const int r = threadIdx.x;
+    if (r < world)
+    {
+        unsigned int v;
+        do
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(my_flags + r) : "memory");
+        } while (v < step);
+    }
+}
+
+int p2p_prepare(nb_sim* h)
+{
+    if (h->posw_buf[1] == nullptr)
+    {
+        NB_CUDA(cudaMalloc(&h->posw_buf[1], h->n * sizeof(float4)));
+        NB_CUDA(cudaMemcpyAsync(h->posw_buf[1], h->posw_buf[0], h->n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (h->p2p_flags == nullptr)
+    {
+        NB_CUDA(cudaMalloc(&h->p2p_flags, NB_MAX_PEERS * sizeof(unsigned int)));
+    }
+    NB_CUDA(cudaMemsetAsync(h->p2p_flags, 0, NB_MAX_PEERS * sizeof(unsigned int), h->stream));
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    return NB_OK;
+}
+
+static PeerTable make_table(const nb_sim* h)
+{
+    PeerTable pt;
+    std::memset(&pt, 0, sizeof(pt));
+    pt.world = h->cfg.world;
+    pt.rank = h->cfg.rank;
+    for (int r = 0; r < h->cfg.world; ++r)
+    {
+        pt.posw[0][r] = static_cast<float4*>(h->peer_posw[0][r]);
+        pt.posw[1][r] = static_cast<float4*>(h->peer_posw[1][r]);
+        pt.flags[r] = static_cast<unsigned int*>(h->peer_flags[r]);
+    }
+    return pt;
+}
+
+int p2p_wait(nb_sim* h)
+{
+    if (h->p2p_step == 0) return NB_OK;
+    k_wait<<<1, 32, 0, h->stream>>>(h->p2p_flags, h->cfg.world, h->p2p_step);
+    NB_CUDA(cudaGetLastError());
+    ++h->last_launches;
+    return NB_OK;
+}
+
+int p2p_kick_drift_push(nb_sim* h, float dt)
+{
+    const PeerTable pt = make_table(h);
+    const bool partials = (h->cfg.mode == NB_MODE_ALLPAIRS);
+    const int blocks = (int)((h->count + 255) / 256);
+    k_kick_drift_push<<<blocks, 256, 0, h->stream>>>(pt, h->posw_cur, (int)h->first, (int)h->count, h->vel,
+                                                     partials ? h->acc_part : nullptr, h->ap_splits, h->acc, (double)dt,
+                                                     h->cfg.position_scale);
+    NB_CUDA(cudaGetLastError());
+    ++h->p2p_step;
+    k_signal<<<1, 32, 0, h->stream>>>(pt, h->p2p_step);
+    NB_CUDA(cudaGetLastError());
+    h->last_launches += 2;
+    h->posw_cur ^= 1;
+    h->posw = h->posw_buf[h->posw_cur];
+    return NB_OK;
+}
+
+void p2p_release(nb_sim* h)
+{
+    if (h->p2p_ipc)
+        for (int r = 0; r < h->cfg.world; ++r)
+        {
+            if (r == h->cfg.rank) continue;
+            for (int b = 0; b < 2; ++b)
+                if (h->peer_posw[b][r]) cudaIpcCloseMemHandle(h->peer_posw[b][r]);
+            if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+        }
+    std::memset(h->peer_posw, 0, sizeof(h->peer_posw));
+    std::memset(h->peer_flags, 0, sizeof(h->peer_flags));
+    h->p2p_attached = false;
+    h->p2p_ipc = false;
+    h->p2p_step = 0;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+int nb_p2p_export(nb_handle h, uint8_t handles[NB_P2P_HANDLE_BYTES])
+{
+    NB_REQUIRE(h != nullptr && handles != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "nb_init_* has not been called");
+    NB_REQUIRE(h->cfg.world <= NB_MAX_PEERS, NB_ERR_ARG, "too many ranks for the peer table");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CHECK(p2p_prepare(h));
+    cudaIpcMemHandle_t m[3];
+    NB_CUDA(cudaIpcGetMemHandle(&m[0], h->posw_buf[0]));
+    NB_CUDA(cudaIpcGetMemHandle(&m[1], h->posw_buf[1]));
+    NB_CUDA(cudaIpcGetMemHandle(&m[2], h->p2p_flags));
+    static_assert(sizeof(m) == NB_P2P_HANDLE_BYTES, "IPC handle size");
+    std::memcpy(handles, m, sizeof(m));
+    return NB_OK;
+}
+
+int nb_p2p_attach(nb_handle h, const uint8_t* all_handles)
+{
+    NB_REQUIRE(h != nullptr && all_handles != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->n > 0 && h->posw_buf[1] != nullptr, NB_ERR_STATE, "call nb_p2p_export first");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    p2p_release(h);
+    for (int r = 0; r < h->cfg.world; ++r)
+    {
+        if (r == h->cfg.rank)
+        {
+            h->peer_posw[0][r] = h->posw_buf[0];
+            h->peer_posw[1][r] = h->posw_buf[1];
+            h->peer_flags[r] = h->p2p_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t m[3];
+        std::memcpy(m, all_handles + (size_t)r * NB_P2P_HANDLE_BYTES, sizeof(m));
+        NB_CUDA(cudaIpcOpenMemHandle(&h->peer_posw[0][r], m[0], cudaIpcMemLazyEnablePeerAccess));
+        NB_CUDA(cudaIpcOpenMemHandle(&h->peer_posw[1][r], m[1], cudaIpcMemLazyEnablePeerAccess));
+        NB_CUDA(cudaIpcOpenMemHandle(&h->peer_flags[r], m[2], cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->p2p_ipc = true;
+    h->p2p_attached = true;
+    return NB_OK;
+}
+
+int nb_p2p_attach_local(nb_handle h, const nb_handle* peers)
+{
+    NB_REQUIRE(h != nullptr && peers != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "nb_init_* has not been called");
+    NB_REQUIRE(h->cfg.world <= NB_MAX_PEERS, NB_ERR_ARG, "too many ranks for the peer table");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    p2p_release(h);
+    for (int r = 0; r < h->cfg.world; ++r)
+    {
+        nb_sim* p = peers[r];
+        NB_REQUIRE(p != nullptr && p->n == h->n && p->cfg.rank == r && p->cfg.world == h->cfg.world, NB_ERR_ARG,
+                   "peer handles must be the ranks 0..world-1 of the same body set");
+        NB_CUDA(cudaSetDevice(p->cfg.device));
+        NB_CHECK(p->posw_buf[1] == nullptr || p->p2p_flags == nullptr ? p2p_prepare(p) : NB_OK);
+        if (p->cfg.device != h->cfg.device)
+        {
+            NB_CUDA(cudaSetDevice(h->cfg.device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(p->cfg.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NB_CUDA(e);
+            cudaGetLastError();
+        }
+        h->peer_posw[0][r] = p->posw_buf[0];
+        h->peer_posw[1][r] = p->posw_buf[1];
+        h->peer_flags[r] = p->p2p_flags;
+    }
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    h->p2p_ipc = false;
+    h->p2p_attached = true;
+    return NB_OK;
+}
+
+}  // extern "C"

@@ -71,3 +71,14 @@ def connect(sim, rank):
     uid = binding.Sim.comm_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, src=0)
     sim.comm_init(uid)
+
+
+def connect_p2p(sim, rank, world):
+    """Fused kick-drift + exchange over NVLink peer memory: all-gather the CUDA IPC handles in rank
+    order (torch.distributed carries 192 opaque bytes per rank), then attach."""
+    import torch.distributed as dist
+    mine = sim.p2p_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    sim.p2p_attach(handles)
+    dist.barrier()

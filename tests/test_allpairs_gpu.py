@@ -203,6 +203,37 @@ def test_sharded_ranks_reproduce_single_gpu_bitwise(pkg, galaxy4096):
     one.close()
 
 
+def test_fused_p2p_exchange_reproduces_single_gpu_bitwise(pkg, galaxy4096):
+    """csrc/p2p.cu: the kick-drift kernel stores every new position into every rank's position
+    array (here: three shard handles on one GPU attached by handle); after k steps the shards hold
+    exactly what a single handle holds."""
+    one = pkg.Sim(mode=pkg.MODE_ALLPAIRS, source_splits=2)
+    one.init(galaxy4096)
+    one.step(0.01, 6)
+    want = galaxy4096.copy()
+    one.read(want)
+    world = 3
+    shards = [pkg.Sim(mode=pkg.MODE_ALLPAIRS, rank=r, world=world, source_splits=2) for r in range(world)]
+    for s in shards:
+        s.init(galaxy4096)
+    for s in shards:
+        s.p2p_attach_local(shards)
+    for _ in range(6):
+        for s in shards:
+            s.step(0.01, 1)              # one host thread drives all ranks, like one step of every process
+    got = galaxy4096.copy()
+    for s in shards:
+        s.read(got)                      # each writes its owned range
+    assert np.array_equal(got["Position"], want["Position"])
+    assert np.array_equal(got["Velocity"], want["Velocity"])
+    # and every rank holds everybody's positions (the exchange happened inside the kernel)
+    acc = np.concatenate([s.accelerations() for s in shards])
+    assert np.array_equal(acc, one.accelerations())
+    for s in shards:
+        s.close()
+    one.close()
+
+
 def test_large_n_sampled_parity(pkg):
     """BASELINE.json configs[1] shape at reduced N (262144): sampled targets against the oracle."""
     n = 1 << 18
