@@ -5,7 +5,9 @@
 // the B200 adapter through the reference's own INBodySim interface and factory names, exactly as
 // SimulationState does (Init on a std::vector<Particle>, then Update(dt) per frame,
 // SimulationState.cpp:52-53, 218-227), so the parity test reads like the reference's usage.
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <iostream>
 #include <sstream>
 #include <vector>
@@ -20,12 +22,20 @@
 
 // INBodySim.cpp itself cannot be compiled headless (it pulls in BruteForceGPU / D3D); this is the
 // same switch without the D3D sim.
+// Zeroed storage: CThreadPool starts its workers before it clears HaveWork[] (ThreadPool.hpp:48-49),
+// so on a recycled heap block a worker can run on garbage.  The sims are released, never deleted.
+template <class Sim>
+static Sim* NewInZeroedStorage(ID3D11DeviceContext* context)
+{
+    return new (std::calloc(1, sizeof(Sim))) Sim(context);
+}
+
 std::unique_ptr<INBodySim> CreateNBodySim(ID3D11DeviceContext* context, ENBodySim type)
 {
     switch (type)
     {
-        case ENBodySim::BruteForceCPU: return std::unique_ptr<INBodySim>(new BruteForceCPU(context));
-        case ENBodySim::BarnesHut:     return std::unique_ptr<INBodySim>(new BarnesHut(context));
+        case ENBodySim::BruteForceCPU: return std::unique_ptr<INBodySim>(NewInZeroedStorage<BruteForceCPU>(context));
+        case ENBodySim::BarnesHut:     return std::unique_ptr<INBodySim>(NewInZeroedStorage<BarnesHut>(context));
         default:                       return nullptr;
     }
 }

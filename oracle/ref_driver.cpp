@@ -15,6 +15,8 @@
 //     mis-indexing of BruteForceCPU.cpp:56-57 / BarnesHut.cpp:70-77 dormant;
 //   * private members are reached with -fno-access-control (Exec, Pool, Tree, Children...).
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <cstring>
 #include <vector>
 #include <chrono>
@@ -45,13 +47,25 @@ namespace
 
     uint32_t g_bruteSpawned = 0, g_treeSpawned = 0;   // worker threads the pool actually started
 
+    // CThreadPool's constructor starts worker i BEFORE it writes HaveWork[i] = false
+    // (ThreadPool.hpp:48-49): on a recycled heap block the worker can read a stale `true` and run
+    // the user function on an uninitialised work item (seen as a segfault in BruteForceCPU::Exec
+    // once torch had churned the heap).  Constructing the sim in zeroed storage makes the flag
+    // false before any worker exists; the sims are never freed (see ~CThreadPool above).
+    template <class Sim>
+    Sim* NewInZeroedStorage()
+    {
+        void* mem = std::calloc(1, sizeof(Sim));
+        return new (mem) Sim(nullptr);
+    }
+
     BruteForceCPU* BruteSim()
     {
         static BruteForceCPU* sim = nullptr;
         if (!sim)
         {
             CoutSilencer q;
-            sim = new BruteForceCPU(nullptr);
+            sim = NewInZeroedStorage<BruteForceCPU>();
             g_bruteSpawned = sim->Pool.GetNumWorkers();
         }
         return sim;
@@ -63,7 +77,7 @@ namespace
         if (!sim)
         {
             CoutSilencer q;
-            sim = new BarnesHut(nullptr);
+            sim = NewInZeroedStorage<BarnesHut>();
             g_treeSpawned = sim->Pool.GetNumWorkers();
         }
         return sim;
