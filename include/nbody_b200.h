@@ -114,6 +114,32 @@ NB_API int nb_init_soa(nb_handle h, const float* pos3, const double* vel3, const
  * AoS buffer, bit-identical to the reference built with g++/libstdc++ (the random engine and
  * distributions are implementation-defined).  Does not need a handle. */
 NB_API int nb_seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale);
+/* All three reference seeders (EParticleSeeder, IParticleSeeder.hpp:12-17; factory
+ * CreateParticleSeeder<T>(particles, type, scale), :29-50) for both record types the reference
+ * instantiates them with: T = Particle (the simulation, SimulationState.cpp:107-110) and
+ * T = LWParticle (the renderer's 32-byte record, Render/Misc/Particle.hpp:20-25; Galaxy.cpp:61,
+ * GalaxyTarget.cpp:109, StarTarget.cpp:209, UniverseTarget.cpp:98).  Output is bit-identical to the
+ * reference built with g++/libstdc++:
+ *   NB_SEEDER_RANDOM      RandomSeeder.cpp:13-40     cube +-500/scale, radial velocity 1e16, mass
+ *                                                    U(1e20,1e30); IGNORES `seed` like the reference
+ *   NB_SEEDER_GALAXY      GalaxySeeder.cpp:43-143    (nb_seed_galaxy_host is this with defaults)
+ *   NB_SEEDER_STARSYSTEM  StarSystemSeeder.cpp:18-55 1e30 star + bodies on +z; IGNORES `seed`, `scale`
+ * `opt` may be NULL (Particle layout, scale 1, colour ranges [0,1]). */
+typedef enum nb_seeder_kind { NB_SEEDER_RANDOM = 0, NB_SEEDER_GALAXY = 1, NB_SEEDER_STARSYSTEM = 2 } nb_seeder_kind;
+typedef enum nb_record_layout { NB_LAYOUT_PARTICLE = 0, NB_LAYOUT_LWPARTICLE = 1 } nb_record_layout;
+#define NB_LW_PARTICLE_STRIDE 32   /* Position float3 @0 | Colour float4 @12 | Scale float @28 */
+#define NB_LW_OFF_SCALE 28
+typedef struct nb_seed_options
+{
+    uint32_t struct_size;   /* = sizeof(nb_seed_options); set by nb_seed_default_options            */
+    int32_t  layout;        /* nb_record_layout                                                     */
+    float    scale;         /* the seeders' `scale` constructor argument (positions are divided)    */
+    float    red[2];        /* GalaxySeeder::SetRedDist(low, hi), clamped to [0,1] (GalaxySeeder.cpp:24-41) */
+    float    green[2];      /* SetGreenDist                                                         */
+    float    blue[2];       /* SetBlueDist                                                          */
+} nb_seed_options;
+NB_API int nb_seed_default_options(nb_seed_options* opt);
+NB_API int nb_seed_host(int kind, void* particles, size_t n, size_t stride, uint64_t seed, const nb_seed_options* opt);
 /* Two-galaxy collision scene used by config 5 (defined by this repo): galaxies seeded
  * with `seed` and `seed+1`, n/2 bodies each, offset by -/+ `separation`/2 along x and approaching
  * each other with `approach_speed` (velocity units). */

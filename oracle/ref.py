@@ -46,6 +46,12 @@ def lib():
         L.ref_particle_offsets.argtypes = [ip]
         L.ref_hardware_workers.restype = C.c_int
         L.ref_seed.argtypes = [vp, sz, C.c_int, C.c_uint64, C.c_float]
+        fp = C.POINTER(C.c_float)
+        L.ref_sizeof_lwparticle.restype = C.c_int
+        L.ref_seed_ex.argtypes = [vp, sz, C.c_int, C.c_uint64, C.c_float, fp]
+        L.ref_seed_lw.argtypes = [vp, sz, C.c_int, C.c_uint64, C.c_float, fp]
+        L.ref_closest_particle.argtypes = [vp, sz, fp]
+        L.ref_closest_particle.restype = C.c_uint64
         L.ref_bruteforce_forces.argtypes = [vp, sz, i64p, sz, dp]
         L.ref_bruteforce_run.argtypes = [vp, sz, C.c_float, C.c_int, C.c_int, ip]
         L.ref_bruteforce_run.restype = C.c_double
@@ -84,6 +90,39 @@ def seed(n, kind=SEED_GALAXY, seed=42, scale=1.0):
     p = np.zeros(n, dtype=PARTICLE_DTYPE)
     lib().ref_seed(_vp(p), n, kind, seed, scale)
     return p
+
+
+# The renderer's record (src/Render/Misc/Particle.hpp:20-25): Position float3, Colour float4, Scale float.
+LWPARTICLE_DTYPE = np.dtype(
+    {"names": ["Position", "Colour", "Scale"], "formats": [("<f4", 3), ("<f4", 4), "<f4"], "offsets": [0, 12, 28],
+     "itemsize": 32}
+)
+
+
+def _rgb(colours):
+    if colours is None:
+        return None
+    a = (C.c_float * 6)(*[float(x) for x in np.asarray(colours).reshape(6)])
+    return a
+
+
+def seed_ex(n, kind=SEED_GALAXY, seed=42, scale=1.0, colours=None, lw=False):
+    """CreateParticleSeeder<T>(v, kind, scale) [+ Set{Red,Green,Blue}Dist] -> Seed(seed) for
+    T = Particle or (lw=True) T = LWParticle.  colours = ((r_lo, r_hi), (g_lo, g_hi), (b_lo, b_hi))."""
+    if lw:
+        assert lib().ref_sizeof_lwparticle() == LWPARTICLE_DTYPE.itemsize
+        p = np.zeros(n, dtype=LWPARTICLE_DTYPE)
+        lib().ref_seed_lw(_vp(p), n, kind, seed, scale, _rgb(colours))
+    else:
+        p = np.zeros(n, dtype=PARTICLE_DTYPE)
+        lib().ref_seed_ex(_vp(p), n, kind, seed, scale, _rgb(colours))
+    return p
+
+
+def closest_particle(p, pos):
+    """Maths::ClosestParticle(pos, particles, &id) -> id."""
+    q = (C.c_float * 3)(*[float(x) for x in pos])
+    return int(lib().ref_closest_particle(_vp(p), len(p), q))
 
 
 def bruteforce_forces(p, targets):

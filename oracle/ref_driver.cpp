@@ -30,6 +30,7 @@
 #include "Sim/Physics.hpp"
 #include "Sim/IParticleSeeder.hpp"
 #include "Core/Event.hpp"
+#include "Core/Maths.hpp"
 
 const DirectX::SimpleMath::Vector3 DirectX::SimpleMath::Vector3::Zero;
 
@@ -106,6 +107,21 @@ namespace
         if (!v.empty()) std::memcpy(aos, v.data(), v.size() * sizeof(Particle));
     }
 
+    template <class T>
+    void SeedWithColours(std::vector<T>& v, int kind, uint64_t seed, float scale, const float* rgb6)
+    {
+        auto seeder = CreateParticleSeeder(v, static_cast<EParticleSeeder>(kind), scale);
+        if (rgb6)
+        {
+            // IParticleSeeder::Set{Red,Green,Blue}Dist (IParticleSeeder.hpp:24-26; only GalaxySeeder
+            // overrides them, GalaxySeeder.cpp:24-41)
+            seeder->SetRedDist(rgb6[0], rgb6[1]);
+            seeder->SetGreenDist(rgb6[2], rgb6[3]);
+            seeder->SetBlueDist(rgb6[4], rgb6[5]);
+        }
+        seeder->Seed(seed);
+    }
+
     std::unique_ptr<Octree> BuildTree(std::vector<Particle>& v, double theta)
     {
         // Same sequence as BarnesHut::Update, src/Sim/BarnesHut.cpp:46-56, with the bounds of
@@ -173,6 +189,35 @@ extern "C"
         auto seeder = CreateParticleSeeder(v, static_cast<EParticleSeeder>(kind), scale);
         seeder->Seed(seed);
         FromVector(v, aos);
+    }
+
+    // The same for the renderer's 32-byte LWParticle (src/Render/Misc/Particle.hpp:20-25), which is
+    // what Galaxy.cpp:61, GalaxyTarget.cpp:109, StarTarget.cpp:209 and UniverseTarget.cpp:98 seed.
+    int ref_sizeof_lwparticle() { return static_cast<int>(sizeof(LWParticle)); }
+
+    void ref_seed_ex(void* aos, size_t n, int kind, uint64_t seed, float scale, const float* rgb6)
+    {
+        std::vector<Particle> v = ToVector(aos, n);
+        SeedWithColours(v, kind, seed, scale, rgb6);
+        FromVector(v, aos);
+    }
+
+    void ref_seed_lw(void* lw, size_t n, int kind, uint64_t seed, float scale, const float* rgb6)
+    {
+        std::vector<LWParticle> v(n);
+        if (n) std::memcpy(static_cast<void*>(v.data()), lw, n * sizeof(LWParticle));
+        SeedWithColours(v, kind, seed, scale, rgb6);
+        if (n) std::memcpy(lw, v.data(), n * sizeof(LWParticle));
+    }
+
+    // Maths::ClosestParticle (src/Core/Maths.hpp:62-85): index of the particle nearest to `pos`
+    // (first minimum of the fp32 squared distance).
+    uint64_t ref_closest_particle(const void* aos, size_t n, const float* pos3)
+    {
+        std::vector<Particle> v = ToVector(aos, n);
+        size_t id = 0;
+        Maths::ClosestParticle(DirectX::SimpleMath::Vector3(pos3[0], pos3[1], pos3[2]), v, &id);
+        return static_cast<uint64_t>(id);
     }
 
     // Forces[target] accumulated by the reference's own BruteForceCPU::Exec for each listed target

@@ -15,6 +15,12 @@ from .binding import (  # noqa: F401
     Sim,
     load,
     seed_galaxy_host,
+    seed_host,
+    SeedOptions,
+    LWPARTICLE_DTYPE,
+    SEEDER_RANDOM,
+    SEEDER_GALAXY,
+    SEEDER_STARSYSTEM,
     seed_collision_host,
     declared_symbols,
 )

@@ -45,6 +45,25 @@ class Config(C.Structure):
     ]
 
 
+class SeedOptions(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("layout", C.c_int32),
+        ("scale", C.c_float),
+        ("red", C.c_float * 2),
+        ("green", C.c_float * 2),
+        ("blue", C.c_float * 2),
+    ]
+
+
+SEEDER_RANDOM, SEEDER_GALAXY, SEEDER_STARSYSTEM = 0, 1, 2
+LAYOUT_PARTICLE, LAYOUT_LWPARTICLE = 0, 1
+# The renderer's 32-byte record (reference src/Render/Misc/Particle.hpp:20-25).
+LWPARTICLE_DTYPE = np.dtype(
+    {"names": ["Position", "Colour", "Scale"], "formats": [("<f4", 3), ("<f4", 4), "<f4"], "offsets": [0, 12, 28],
+     "itemsize": 32}
+)
+
 _lib = None
 
 
@@ -71,6 +90,8 @@ def load():
     L.nb_init_aos.argtypes = [vp, vp, sz, sz]
     L.nb_init_soa.argtypes = [vp, vp, vp, vp, sz]
     L.nb_seed_galaxy_host.argtypes = [vp, sz, sz, C.c_uint64, f32]
+    L.nb_seed_default_options.argtypes = [C.POINTER(SeedOptions)]
+    L.nb_seed_host.argtypes = [C.c_int, vp, sz, sz, C.c_uint64, C.POINTER(SeedOptions)]
     L.nb_seed_collision_host.argtypes = [vp, sz, sz, C.c_uint64, f32, f32, f64]
     L.nb_seed_galaxy_device.argtypes = [vp, sz, C.c_uint64, f32]
     L.nb_step.argtypes = [vp, f32, C.c_int]
@@ -110,6 +131,22 @@ def seed_galaxy_host(n, seed=42, scale=1.0):
     """GalaxySeeder<Particle>(particles, scale).Seed(seed) -- reference GalaxySeeder.cpp:43-80."""
     p = np.zeros(n, dtype=PARTICLE_DTYPE)
     _check(load().nb_seed_galaxy_host(p.ctypes.data, n, PARTICLE_DTYPE.itemsize, seed, scale))
+    return p
+
+
+def seed_host(kind, n, seed=0, scale=1.0, colours=None, lw=False):
+    """CreateParticleSeeder<T>(particles, kind, scale)->Seed(seed) -- reference IParticleSeeder.hpp:29-50 --
+    for T = Particle or (lw=True) T = LWParticle; colours = ((r_lo, r_hi), (g_lo, g_hi), (b_lo, b_hi))
+    are the GalaxySeeder Set{Red,Green,Blue}Dist ranges."""
+    dtype = LWPARTICLE_DTYPE if lw else PARTICLE_DTYPE
+    p = np.zeros(n, dtype=dtype)
+    o = SeedOptions()
+    _check(load().nb_seed_default_options(C.byref(o)))
+    o.layout = LAYOUT_LWPARTICLE if lw else LAYOUT_PARTICLE
+    o.scale = scale
+    if colours is not None:
+        (o.red[0], o.red[1]), (o.green[0], o.green[1]), (o.blue[0], o.blue[1]) = colours
+    _check(load().nb_seed_host(kind, p.ctypes.data, n, dtype.itemsize, seed, C.byref(o)))
     return p
 
 

@@ -1,4 +1,7 @@
-// Host galaxy seeder: the procedural initial conditions that feed the simulation.
+// Host particle seeders: the procedural initial conditions that feed the simulation
+// (IParticleSeeder, reference src/Sim/IParticleSeeder.hpp:12-50): GalaxySeeder, RandomSeeder and
+// StarSystemSeeder, each for the reference's two record types (Particle, 104 bytes, and the
+// renderer's LWParticle, 32 bytes -- src/Render/Misc/Particle.hpp:8-25).
 //
 // Follows GalaxySeeder<Particle>::Seed / CreateSpiralArm / AddParticle
 // (reference src/Sim/GalaxySeeder.cpp:43-80, 109-143, 83-106) and produces, bit for bit, what the
@@ -172,18 +175,51 @@ V3 transform(V3 v, const Rot& M)
     return {r[0] / r[3], r[1] / r[3], r[2] / r[3]};
 }
 
-struct Seeder
+// One output record in either of the reference's layouts.  For LWParticle the velocity, mass,
+// forces and original colour setters are no-ops (the SFINAE AddParticle* overloads,
+// Particle.hpp:48-82) but their ARGUMENTS are still evaluated, so the random draws are the same.
+struct Writer
 {
     unsigned char* out;
-    size_t n, stride;
+    size_t stride;
+    int layout;
+
+    void put(size_t i, V3 p, const float col[4], const double vel[3], double mass) const
+    {
+        unsigned char* rec = out + i * stride;
+        const float pos3[3] = {p.x, p.y, p.z};
+        std::memcpy(rec + 0, pos3, sizeof(pos3));
+        std::memcpy(rec + 12, col, 16);
+        if (layout == NB_LAYOUT_LWPARTICLE)
+        {
+            const float one = 1.0f;   // AddParticleScale(p, 1.0f)
+            std::memcpy(rec + NB_LW_OFF_SCALE, &one, sizeof(one));
+            return;
+        }
+        const double zero[3] = {0.0, 0.0, 0.0};
+        std::memcpy(rec + 28, col, 16);
+        std::memcpy(rec + NB_OFF_VELOCITY, vel, 24);
+        std::memcpy(rec + NB_OFF_FORCES, zero, sizeof(zero));
+        std::memcpy(rec + NB_OFF_MASS, &mass, sizeof(mass));
+    }
+};
+
+inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+
+struct Seeder
+{
+    Writer w;
+    size_t n;
     float scale;
     size_t local = 0;
     Lcg gen;
     NormalF distz{0.0f, 16.0f};
     Rot orientation;
+    // DistR / DistG / DistB, GalaxySeeder.cpp:14-16; Set{Red,Green,Blue}Dist clamp to [0,1] (:24-41).
+    float red[2] = {0.0f, 1.0f}, green[2] = {0.0f, 1.0f}, blue[2] = {0.0f, 1.0f};
 
-    Seeder(void* p, size_t n_, size_t stride_, uint64_t seed, float scale_)
-        : out(static_cast<unsigned char*>(p)), n(n_), stride(stride_), scale(scale_), gen((uint32_t)seed)
+    Seeder(void* p, size_t n_, size_t stride_, int layout_, uint64_t seed, float scale_)
+        : w{static_cast<unsigned char*>(p), stride_, layout_}, n(n_), scale(scale_), gen((uint32_t)seed)
     {
     }
 
@@ -191,23 +227,15 @@ struct Seeder
     bool add_particle(V3 pos, double vx, double vy, double vz, double mass)
     {
         if (local >= n) return false;
-        unsigned char* rec = out + local * stride;
         const V3 scaled = {pos.x / scale, pos.y / scale, pos.z / scale};
         const V3 p = transform(scaled, orientation);
         // Color(DistR(Gen), DistG(Gen), DistB(Gen)): g++ evaluates the arguments right to left.
-        const float b = uniform_f(gen, 0.0f, 1.0f);
-        const float g = uniform_f(gen, 0.0f, 1.0f);
-        const float r = uniform_f(gen, 0.0f, 1.0f);
-        const float pos3[3] = {p.x, p.y, p.z};
+        const float b = uniform_f(gen, blue[0], blue[1]);
+        const float g = uniform_f(gen, green[0], green[1]);
+        const float r = uniform_f(gen, red[0], red[1]);
         const float col[4] = {r, g, b, 1.0f};
         const double vel[3] = {vx, vy, vz};
-        const double zero[3] = {0.0, 0.0, 0.0};
-        std::memcpy(rec + 0, pos3, sizeof(pos3));
-        std::memcpy(rec + 12, col, sizeof(col));
-        std::memcpy(rec + 28, col, sizeof(col));
-        std::memcpy(rec + NB_OFF_VELOCITY, vel, sizeof(vel));
-        std::memcpy(rec + NB_OFF_FORCES, zero, sizeof(zero));
-        std::memcpy(rec + NB_OFF_MASS, &mass, sizeof(mass));
+        w.put(local, p, col, vel, mass);
         ++local;
         return true;
     }
@@ -278,6 +306,65 @@ struct Seeder
     }
 };
 
+
+// RandomSeeder<T>::Seed, reference src/Sim/RandomSeeder.cpp:13-40.  The reference constructs a
+// fresh default_random_engine and never uses its `seed` argument; so does this.
+void seed_random(const Writer& w, size_t n, float scale)
+{
+    Lcg gen(1u);   // std::default_random_engine{} == minstd_rand0 with default_seed 1
+    for (size_t i = 0; i < n; ++i)
+    {
+        // uniform_real_distribution<double>(-500.0f, 500.0), narrowed to float, then / Scale
+        V3 p;
+        p.x = (float)uniform_d(gen, -500.0, 500.0) / scale;
+        p.y = (float)uniform_d(gen, -500.0, 500.0) / scale;
+        p.z = (float)uniform_d(gen, -500.0, 500.0) / scale;
+        const V3 nrm = normalize(p);
+        // Vec3d vel(normal); vel *= 10000000000000000.0f  (double * float-literal-as-double)
+        const double k = (double)10000000000000000.0f;
+        const double vel[3] = {(double)nrm.x * k, (double)nrm.y * k, (double)nrm.z * k};
+        const double mass = uniform_d(gen, 1e20, 1e30);
+        // Color(dist_col, dist_col, dist_col, 1.0f): arguments right to left under g++.
+        const float b = uniform_f(gen, 0.2f, 1.0f);
+        const float g = uniform_f(gen, 0.2f, 1.0f);
+        const float r = uniform_f(gen, 0.2f, 1.0f);
+        const float col[4] = {r, g, b, 1.0f};
+        w.put(i, p, col, vel, mass);
+    }
+}
+
+// StarSystemSeeder<T>::Seed, reference src/Sim/StarSystemSeeder.cpp:18-55: a 1e30 star at the
+// origin and n-1 bodies strung along +z with velocities in the xy plane.  Ignores `seed` and
+// `scale` like the reference.
+void seed_starsystem(const Writer& w, size_t n)
+{
+    const double AU = 1.15e12, M = 1000.0, StarSystemScale = 20 * AU;   // Physics.hpp:11-16
+    {
+        const float col[4] = {0.6f, 1.0f, 1.0f, 1.0f};
+        const double vel[3] = {0.0, 0.0, 0.0};
+        w.put(0, V3{0.f, 0.f, 0.f}, col, vel, 1e30);
+    }
+    Lcg gen(1u);
+    const double rad_lo = 4.0 * AU * M, rad_hi = 7.0 * AU * M;
+    const double vel_lo = 1 * AU * M, vel_hi = 5 * AU * M;
+    for (size_t i = 1; i < n; ++i)
+    {
+        V3 p = {0.f, 0.f, 0.f};
+        p.z = (float)(uniform_d(gen, rad_lo, rad_hi) / StarSystemScale);
+        // Vec3d vel(dist_vel(gen), dist_vel(gen) / 20.0, 0): constructor arguments right to left.
+        const double vy = uniform_d(gen, vel_lo, vel_hi) / 20.0;
+        const double vx = uniform_d(gen, vel_lo, vel_hi);
+        const double vel[3] = {vx, vy, 0.0};
+        const double mass = uniform_d(gen, 1e10, 1e26);
+        // Color(dist_red, dist_col, dist_col, 1.0f), right to left.
+        const float b = uniform_f(gen, 0.2f, 1.0f);
+        const float g = uniform_f(gen, 0.2f, 1.0f);
+        const float r = uniform_f(gen, 0.0f, 0.4f);
+        const float col[4] = {r, g, b, 1.0f};
+        w.put(i, p, col, vel, mass);
+    }
+}
+
 }  // namespace
 
 namespace nb
@@ -285,12 +372,78 @@ namespace nb
 
 int seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale)
 {
-    Seeder s(particles, n, stride, seed, scale);
+    Seeder s(particles, n, stride, NB_LAYOUT_PARTICLE, seed, scale);
     s.seed();
     return NB_OK;
 }
 
 }  // namespace nb
+
+extern "C" int nb_seed_default_options(nb_seed_options* opt)
+{
+    if (opt == nullptr)
+    {
+        nb::set_error("nb_seed_default_options: null argument");
+        return NB_ERR_ARG;
+    }
+    std::memset(opt, 0, sizeof(*opt));
+    opt->struct_size = (uint32_t)sizeof(*opt);
+    opt->layout = NB_LAYOUT_PARTICLE;
+    opt->scale = 1.0f;
+    opt->red[1] = opt->green[1] = opt->blue[1] = 1.0f;
+    return NB_OK;
+}
+
+extern "C" int nb_seed_host(int kind, void* particles, size_t n, size_t stride, uint64_t seed,
+                            const nb_seed_options* opt)
+{
+    nb_seed_options o;
+    nb_seed_default_options(&o);
+    if (opt != nullptr)
+    {
+        if (opt->struct_size != sizeof(nb_seed_options))
+        {
+            nb::set_error("nb_seed_host: nb_seed_options.struct_size mismatch");
+            return NB_ERR_ARG;
+        }
+        o = *opt;
+    }
+    const size_t min_stride = (o.layout == NB_LAYOUT_LWPARTICLE) ? NB_LW_PARTICLE_STRIDE : NB_PARTICLE_STRIDE;
+    if ((particles == nullptr && n > 0) || (o.layout != NB_LAYOUT_PARTICLE && o.layout != NB_LAYOUT_LWPARTICLE) ||
+        stride < min_stride || stride % 4 != 0 || !(o.scale != 0.0f))
+    {
+        nb::set_error("nb_seed_host: bad argument (null buffer, unknown layout, stride below the record size, or zero scale)");
+        return NB_ERR_ARG;
+    }
+    const Writer w{static_cast<unsigned char*>(particles), stride, o.layout};
+    switch (kind)
+    {
+        case NB_SEEDER_RANDOM:
+            seed_random(w, n, o.scale);
+            return NB_OK;
+        case NB_SEEDER_GALAXY:
+        {
+            Seeder s(particles, n, stride, o.layout, seed, o.scale);
+            s.red[0] = clamp01(o.red[0]), s.red[1] = clamp01(o.red[1]);
+            s.green[0] = clamp01(o.green[0]), s.green[1] = clamp01(o.green[1]);
+            s.blue[0] = clamp01(o.blue[0]), s.blue[1] = clamp01(o.blue[1]);
+            s.seed();
+            return NB_OK;
+        }
+        case NB_SEEDER_STARSYSTEM:
+            if (n == 0)
+            {
+                // the reference writes Particles[0] unconditionally (StarSystemSeeder.cpp:20)
+                nb::set_error("nb_seed_host: the star-system seeder needs at least one particle");
+                return NB_ERR_ARG;
+            }
+            seed_starsystem(w, n);
+            return NB_OK;
+        default:
+            nb::set_error("nb_seed_host: unknown seeder kind");
+            return NB_ERR_ARG;
+    }
+}
 
 extern "C" int nb_seed_collision_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale,
                                       float separation, double approach_speed)
