@@ -14,8 +14,8 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisi
 # -fmad stays on for device code (the kernels state where fusion matters); host seeder must not fuse.
 CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -fvisibility=hidden -I/usr/local/cuda/include
 
-CU_SRCS := $(SRC)/nb_api.cu $(SRC)/integrate.cu $(SRC)/tree.cu $(SRC)/energy.cu $(SRC)/probe.cu $(SRC)/seed_device.cu $(SRC)/p2p.cu
-CPP_SRCS := $(SRC)/seed_host.cpp $(SRC)/nccl_dl.cpp
+CU_SRCS := $(SRC)/nb_api.cu $(SRC)/integrate.cu $(SRC)/tree.cu $(SRC)/energy.cu $(SRC)/probe.cu $(SRC)/seed_device.cu $(SRC)/p2p.cu $(SRC)/query.cu
+CPP_SRCS := $(SRC)/seed_host.cpp $(SRC)/nccl_dl.cpp $(SRC)/nbody_io.cpp
 CU_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
 CPP_OBJS := $(patsubst $(SRC)/%.cpp,$(OBJ)/%.o,$(CPP_SRCS))
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/nbody_b200.h

@@ -11,6 +11,9 @@ One "step" is one INBodySim::Update on device-resident state: force pass + fused
                   ranks = strong scaling]
     allpairs_16m  all-pairs fp32, N = 2^24 sharded over the ranks (configs[2])
     bh_1m/bh_16m  Barnes-Hut theta = 0.5, per-step rebuild, dt = 0.02/60 (configs[3])
+    collision_64m two-galaxy collision, N = 2^26, Barnes-Hut theta = 0.5 (configs[4]; run it with
+                  --gpus 8 --steps 1000): adds an "energy" object with the drift of the conserved
+                  quantity between the first and the last step (collision_1m: same scene, 2^20)
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own CPU path
 (oracle/_ref, else the C port) on the host cores on a bounded sample of the same workload.
@@ -40,7 +43,15 @@ WORKLOADS = {
                   desc="Barnes-Hut theta=0.5 N=1048576 single spiral galaxy, per-step LBVH rebuild, dt=0.02/60"),
     "bh_16m": dict(mode="bh", n=1 << 24, dt=0.02 / 60, seed=42, theta=0.5,
                    desc="Barnes-Hut theta=0.5 N=16777216 single spiral galaxy, per-step LBVH rebuild, dt=0.02/60"),
+    # BASELINE.json configs[4]: two-galaxy collision (seeds 42 / 43, centres 2000 apart, approaching at
+    # 2e16), Barnes-Hut theta = 0.5, dt = 0.02/60; run with --steps 1000.  The energy of the conserved
+    # quantity is estimated before the first and after the last step from a fixed sample of bodies.
+    "collision_64m": dict(mode="bh", n=1 << 26, dt=0.02 / 60, seed=42, theta=0.5, scene="collision", energy_stride=16384,
+                          desc="two-galaxy collision N=67108864 (GalaxySeeder seeds 42/43), Barnes-Hut theta=0.5, per-step LBVH rebuild, dt=0.02/60"),
+    "collision_1m": dict(mode="bh", n=1 << 20, dt=0.02 / 60, seed=42, theta=0.5, scene="collision", energy_stride=256,
+                         desc="two-galaxy collision N=1048576 (GalaxySeeder seeds 42/43), Barnes-Hut theta=0.5, per-step LBVH rebuild, dt=0.02/60"),
 }
+COLLISION = dict(separation=2000.0, approach_speed=2e16)     # the scene of tests/golden/energy_drift_n4096.npz
 
 FLOPS_PER_INTERACTION = 20   # 3 sub, 5 d^2, 1 add S, 1 sqrt, 1 div, 3 div, 3 mul, 3 add
 
@@ -153,13 +164,26 @@ def cpu_sample(p, mode, seconds, theta=0.5):
     return per_target * n / (secs * n / len(targets)), 1, f"C port: octree build + walk of {len(targets)} sampled targets, {secs:.2f} s, scaled", "port"
 
 
+def seed_workload(pkg, wl, out=None):
+    """The workload's bodies through the product's bit-exact host seeders (into `out` if given)."""
+    n = wl["n"]
+    if wl.get("scene") == "collision":
+        p = pkg.seed_collision_host(n, wl["seed"], 1.0, **COLLISION)
+    else:
+        p = pkg.seed_galaxy_host(n, wl["seed"], 1.0)
+    if out is None:
+        return p
+    out[:] = p
+    return out
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's CPU implementation on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     pkg = importlib.import_module("procedural-universe_b200")
-    p = pkg.seed_galaxy_host(wl["n"], wl["seed"], 1.0)
+    p = seed_workload(pkg, wl)
     rates, desc, cores, kind = [], "", 1, "port"
     per_step_seconds = 4.0
     for i in range(args.warmup + args.steps):
@@ -224,9 +248,12 @@ def main():
     mode = pkg.MODE_ALLPAIRS if wl["mode"] == "allpairs" else pkg.MODE_BARNESHUT
 
     # pinned host AoS array: the caller's std::vector<Particle>
-    host = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
-    particles = host.numpy().view(pkg.PARTICLE_DTYPE)
-    particles[:] = pkg.seed_galaxy_host(n, wl["seed"], 1.0)
+    if n * 104 <= (2 << 30) and not args.no_e2e:
+        host = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
+        particles = seed_workload(pkg, wl, host.numpy().view(pkg.PARTICLE_DTYPE))
+    else:
+        particles = seed_workload(pkg, wl)      # multi-GB scenes: pageable, the e2e leg is not run on them
+        args.no_e2e = True
 
     stream = torch.cuda.current_stream()
     sim = pkg.Sim(mode=mode, theta=wl.get("theta", 2.0), device=local_rank, rank=rank, world=world,
@@ -258,6 +285,18 @@ def main():
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    def total_energy():
+        """(kinetic, potential estimate, samples) summed over the ranks; see nb_energy_sampled."""
+        ke, pe, ns = sim.energy_sampled(wl["energy_stride"])
+        t = torch.tensor([ke, pe, float(ns)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t[0].item()), float(t[1].item()), int(t[2].item())
+
+    energy = None
+    if "energy_stride" in wl:
+        energy = {"start": total_energy()}
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -287,6 +326,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+
+    if energy is not None:
+        energy["end"] = total_energy()
 
     walk, build_ms = None, None
     if wl["mode"] == "bh":
@@ -377,9 +419,21 @@ def main():
                            "api": "nb_update_aos on a pinned 104-byte Particle array (INBodySim::Update contract)"}
         line["clocks"] = clocks
         line["parity"] = parity
+        if energy is not None:
+            (k0, p0, ns), (k1, p1, _) = energy["start"], energy["end"]
+            ref_drift = None
+            try:
+                ref_drift = float(np.load(os.path.join(ROOT, "tests", "golden", "energy_drift_n4096.npz"))["drift"][-1])
+            except Exception:
+                pass
+            line["energy"] = {
+                "steps": args.warmup + args.steps, "kinetic": [k0, k1], "potential": [p0, p1],
+                "drift": abs((k1 + p1) - (k0 + p0)) / abs(k0 + p0),
+                "estimator": f"E = sum 1/2 m v^2 (exact) + 2.3e13 * sum U(r) estimated from {ns} bodies (every {wl['energy_stride']}th) x all sources, same bodies at both times",
+                "reference_drift_n4096_1000_steps": ref_drift,
+            }
         if world == 1 and not args.no_cpu_baseline:
-            p = np.array(particles)   # state after the timed steps; the rate does not depend on it
-            p = pkg.seed_galaxy_host(n, wl["seed"], 1.0)
+            p = seed_workload(pkg, wl)   # the initial state (particles now holds the state after the e2e steps)
             rate, cores, desc, kind = cpu_sample(p, wl["mode"], 12.0, wl.get("theta", 0.5))
             line["cpu_baseline"] = {"value": rate, "unit": unit, "cores": cores, "kind": kind, "sample": desc,
                                     "host_cores": host_cores()}

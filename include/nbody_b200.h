@@ -200,6 +200,30 @@ NB_API int nb_get_walk_stats(nb_handle h, uint64_t stats3[3]);
  * E = sum 1/2 m v^2 + position_scale * sum_{i<j} U(r), U = -(G ma mb / sqrt(S)) atan(sqrt(S)/r),
  * potential by exact pair sum over owned targets x all sources (O(N^2/world)). */
 NB_API int nb_energy(nb_handle h, double* kinetic, double* potential);
+/* The same quantity where the exact pair sum is out of reach (config 5, 64 M bodies): kinetic energy
+ * exactly over the owned bodies, potential estimated from the owned bodies whose GLOBAL index is a
+ * multiple of `stride`, each against all sources, scaled by `stride`.  stride = 1 is the exact sum.
+ * The sample is a fixed set of bodies, so drift |E(t)-E(0)|/|E(0)| compares the same bodies. */
+NB_API int nb_energy_sampled(nb_handle h, size_t stride, double* kinetic, double* potential, size_t* nsamples);
+
+/* ---- queries ---------------------------------------------------------------------------------- */
+/* Maths::ClosestParticle(pos, particles, &id) -- Core/Maths.hpp:62-85, pinned by the reference's
+ * test/MathsTests.cpp:4-33 -- on the handle's CURRENT device-resident positions: index of the body
+ * with the smallest fp32 DistanceSquared to `pos`; the first index wins ties (strict <, scan in
+ * index order); 0 when no body has a finite distance below FLT_MAX.  dist_sq may be NULL. */
+NB_API int nb_closest_particle(nb_handle h, const float pos[3], size_t* index, float* dist_sq);
+
+/* ---- .nbody particle files (host I/O, no handle) ------------------------------------------------ */
+/* The reference's checkpoint format: the raw std::vector<Particle>, 104 bytes per body, no header
+ * (writer SimulationState.cpp:317-331, reader :229-277). */
+NB_API int nb_nbody_save(const char* path, const void* particles, size_t n, size_t stride);
+/* Number of whole records in the file. */
+NB_API int nb_nbody_count(const char* path, size_t* n);
+/* Reads up to `capacity` records; a trailing partial record is dropped like the reference's read
+ * loop does.  recentre != 0 applies InitParticlesFromFile's mass-weighted recentring (:252-270). */
+NB_API int nb_nbody_load(const char* path, void* particles, size_t capacity, size_t stride, size_t* n_read, int recentre);
+/* The recentring alone: Position -= (float3)(sum pos*Mass / sum Mass), sums in index order. */
+NB_API int nb_nbody_recentre(void* particles, size_t n, size_t stride);
 
 /* ---- multi-GPU plumbing ---------------------------------------------------------------------- */
 /* One handle per process/GPU.  The host (torch.distributed, MPI, ...) moves 128 opaque bytes from

@@ -104,3 +104,32 @@ def energy(p):
     ke, pe = C.c_double(), C.c_double()
     lib().port_energy(p.ctypes.data, len(p), C.byref(ke), C.byref(pe))
     return ke.value, pe.value
+
+
+def recentre(p):
+    """InitParticlesFromFile's recentring (reference SimulationState.cpp:252-270) restated in numpy:
+    TotalMass accumulates in `long double`, the weighted position sums in double, both in index
+    order (cumsum is a sequential scan); CentreOfMass /= (double)TotalMass; Position -= (float3)centre."""
+    q = p.copy()
+    if len(q) == 0:
+        return q
+    m = q["Mass"]
+    total = float(np.cumsum(m.astype(np.longdouble))[-1])
+    pos = q["Position"].astype(np.float64)
+    with np.errstate(all="ignore"):
+        c = np.array([np.cumsum(pos[:, k] * m)[-1] for k in range(3)]) / total
+        q["Position"] = q["Position"] - c.astype(np.float32)
+    return q
+
+
+def closest_particle(p, pos):
+    """Maths::ClosestParticle (reference Core/Maths.hpp:62-85): fp32 ((dx*dx + dy*dy) + dz*dz), strict <
+    from FLT_MAX in index order -> first index among equal minima, 0 when nothing qualifies."""
+    q = np.asarray(pos, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        d = q[None, :] - p["Position"]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    ok = d2 < np.finfo(np.float32).max
+    if not ok.any():
+        return 0
+    return int(np.argmin(np.where(ok, d2, np.inf)))

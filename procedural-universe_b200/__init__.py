@@ -23,4 +23,7 @@ from .binding import (  # noqa: F401
     SEEDER_STARSYSTEM,
     seed_collision_host,
     declared_symbols,
+    save_nbody,
+    load_nbody,
+    recentre,
 )

@@ -107,6 +107,12 @@ def load():
     L.nb_get_tree.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     L.nb_get_walk_stats.argtypes = [vp, vp]
     L.nb_energy.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
+    L.nb_energy_sampled.argtypes = [vp, sz, C.POINTER(f64), C.POINTER(f64), C.POINTER(sz)]
+    L.nb_closest_particle.argtypes = [vp, C.POINTER(f32), C.POINTER(sz), C.POINTER(f32)]
+    L.nb_nbody_save.argtypes = [C.c_char_p, vp, sz, sz]
+    L.nb_nbody_count.argtypes = [C.c_char_p, C.POINTER(sz)]
+    L.nb_nbody_load.argtypes = [C.c_char_p, vp, sz, sz, C.POINTER(sz), C.c_int]
+    L.nb_nbody_recentre.argtypes = [vp, sz, sz]
     L.nb_comm_unique_id.argtypes = [vp]
     L.nb_comm_init.argtypes = [vp, vp]
     L.nb_device_posw.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
@@ -155,6 +161,27 @@ def seed_collision_host(n, seed=42, scale=1.0, separation=2000.0, approach_speed
     _check(load().nb_seed_collision_host(p.ctypes.data, n, PARTICLE_DTYPE.itemsize, seed, scale,
                                          separation, approach_speed))
     return p
+
+
+def save_nbody(path, particles):
+    """Writes the reference's .nbody file (raw 104-byte Particle records, SimulationState.cpp:317-331)."""
+    p = np.ascontiguousarray(particles)
+    _check(load().nb_nbody_save(os.fsencode(path), p.ctypes.data, len(p), p.dtype.itemsize))
+
+
+def load_nbody(path, recentre=True):
+    """InitParticlesFromFile (SimulationState.cpp:229-277): all whole records, recentred on the centre of mass."""
+    n = C.c_size_t()
+    _check(load().nb_nbody_count(os.fsencode(path), C.byref(n)))
+    p = np.zeros(n.value, dtype=PARTICLE_DTYPE)
+    got = C.c_size_t()
+    _check(load().nb_nbody_load(os.fsencode(path), p.ctypes.data, len(p), PARTICLE_DTYPE.itemsize, C.byref(got), int(recentre)))
+    return p[: got.value]
+
+
+def recentre(particles):
+    _check(load().nb_nbody_recentre(particles.ctypes.data, len(particles), particles.dtype.itemsize))
+    return particles
 
 
 class _CudaArray:
@@ -288,6 +315,19 @@ class Sim:
         ke, pe = C.c_double(), C.c_double()
         _check(self._L.nb_energy(self._h, C.byref(ke), C.byref(pe)))
         return ke.value, pe.value
+
+    def closest_particle(self, pos):
+        """Maths::ClosestParticle on the device-resident positions -> (index, distance squared)."""
+        q = (C.c_float * 3)(*[float(x) for x in pos])
+        idx, d = C.c_size_t(), C.c_float()
+        _check(self._L.nb_closest_particle(self._h, q, C.byref(idx), C.byref(d)))
+        return idx.value, d.value
+
+    def energy_sampled(self, stride):
+        """(kinetic, potential estimate, samples): see nb_energy_sampled."""
+        ke, pe, ns = C.c_double(), C.c_double(), C.c_size_t()
+        _check(self._L.nb_energy_sampled(self._h, C.c_size_t(stride), C.byref(ke), C.byref(pe), C.byref(ns)))
+        return ke.value, pe.value, ns.value
 
     # --- multi-GPU plumbing
     @staticmethod

@@ -544,7 +544,19 @@ int nb_energy(nb_handle h, double* kinetic, double* potential)
     NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
     NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
     NB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->p2p_attached) NB_CHECK(p2p_wait(h));
     return nb::energy(h, kinetic, potential);
+}
+
+int nb_energy_sampled(nb_handle h, size_t stride, double* kinetic, double* potential, size_t* nsamples)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(stride >= 1, NB_ERR_ARG, "stride must be >= 1");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_REQUIRE(h->exchanged, NB_ERR_STATE, "positions of remote ranks are stale");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->p2p_attached) NB_CHECK(p2p_wait(h));
+    return nb::energy_sampled(h, stride, kinetic, potential, nsamples);
 }
 
 int nb_comm_unique_id(uint8_t id[128]) { return nb::comm_unique_id(id); }

@@ -148,6 +148,7 @@ int seed_galaxy_device(nb_sim* h, size_t n, uint64_t seed, float scale);
 
 // energy.cu
 int energy(nb_sim* h, double* ke, double* pe);
+int energy_sampled(nb_sim* h, size_t stride, double* ke, double* pe, size_t* nsamples);
 
 // probe.cu
 int probe_fp32_peak(nb_sim* h, double* flops);
