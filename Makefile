@@ -1,5 +1,5 @@
 # Builds the product library (sm_100a only), the tuner, and the oracle pieces.
-#   make            -> procedural-universe_b200/lib/libnbody_b200.so
+#   make            -> procedural-universe_b200/lib/libnbody_b200.so, procedural-universe_b200/bin/nbody_headless
 #   make tools      -> tools/tune_allpairs
 #   make oracle     -> oracle/_build/libnbody_port.so (+ oracle/_ref/libpu_ref.so when /root/reference exists)
 NVCC ?= /usr/local/cuda/bin/nvcc
@@ -20,7 +20,13 @@ CU_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
 CPP_OBJS := $(patsubst $(SRC)/%.cpp,$(OBJ)/%.o,$(CPP_SRCS))
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/nbody_b200.h
 
-all: $(LIB)
+BIN := $(PKG)/bin/nbody_headless
+
+all: $(LIB) $(BIN)
+
+$(BIN): $(PKG)/host/nbody_headless.cpp include/nbody_b200.h $(LIB)
+	@mkdir -p $(PKG)/bin
+	$(CXX) -O2 -std=c++17 -Iinclude -o $@ $< -L$(PKG)/lib -lnbody_b200 -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -43,6 +49,6 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(OBJ) $(PKG)/lib tools/tune_allpairs
+	rm -rf $(OBJ) $(PKG)/lib $(PKG)/bin tools/tune_allpairs
 
 .PHONY: all tools oracle clean

@@ -44,13 +44,12 @@ struct TreeBuffers
     uint32_t* hist = nullptr;       // radix-sort block histograms
     size_t hist_words = 0;
     uint32_t* counters = nullptr;   // [0] in-bounds bodies, [1..] scratch
-    int32_t* child = nullptr;       // [2][n-1] left/right child of internal node (>=0 internal, <0 ~leaf)
+    int2* child = nullptr;          // [n-1] {left, right} child of internal node (< n internal, >= n leaf slot + n)
     int32_t* parent = nullptr;      // [2n-1]   parent of internal nodes then of leaves
     int32_t* prefix = nullptr;      // [n-1]    common-prefix length in bits (0..63; 64+ = duplicate codes)
     int32_t* range = nullptr;       // [2][n-1] first/last sorted slot covered
     uint32_t* flags = nullptr;      // [n-1]    arrival counters of the bottom-up pass
-    double* nmass = nullptr;        // [2n-1]   mass  (internal nodes, then leaves)
-    double* ncom = nullptr;         // [3][2n-1] mass-weighted position sums -> centre of mass
+    double* nsum = nullptr;         // [n-1][4] {G M, G M x, G M y, G M z} of internal nodes, fp64, one 32-byte record each
     float4* walk_a = nullptr;       // [2n-1] {com.x, com.y, com.z, G*M}
     int4* walk_b = nullptr;         // [2n-1] {open threshold (float bits), first slot, next-if-open, next-if-skip}
     unsigned long long* stats = nullptr;   // [3] accepted cells, pair evals, node visits

@@ -40,7 +40,7 @@ constexpr int kEnd = -1;
 enum { C_INBOUNDS = 0, C_TOTAL = 1, C_WORDS = 8 };
 
 // ------------------------------------------------------------------------------------------------
-// K3: Morton codes.  Same comparison descent as the CPU restatement (oracle/nbody_port.c,
+// K3: Morton codes.  Same cells as the comparison descent of the CPU restatement (oracle/nbody_port.c,
 // port_morton_one): cell corners -B + k * 2B / 2^level are exact in fp64, so the digits are the
 // ones Octree::Add's Contains() tests select.  Bodies outside the root get the key ~0.
 // ------------------------------------------------------------------------------------------------
@@ -55,24 +55,21 @@ __device__ __forceinline__ unsigned long long spread3(unsigned int v)
     return x;
 }
 
-__device__ __forceinline__ unsigned int axis_cell(double p, double B)
+// Cell index of p along one axis at level 21: the k with lo(k) <= p < lo(k+1), lo(k) = -B + k * cell,
+// cell = 2B / 2^21.  B is a float, so k * cell (<= 45 significant bits) and lo(k) are exact in fp64 and
+// this is the same k the 21-step comparison descent of the restatement (port_morton_one) arrives at:
+// estimate by one multiplication, then settle with the exact corner comparisons.
+__device__ __forceinline__ unsigned int axis_cell(double p, double B, double cell, double inv_cell)
 {
-    double lo = -B, size = 2.0 * B;
-    unsigned int q = 0;
-#pragma unroll
-    for (int l = 0; l < kLevels; ++l)
-    {
-        size *= 0.5;
-        const double mid = lo + size;
-        const bool up = p >= mid;
-        q = (q << 1) | (up ? 1u : 0u);
-        if (up) lo = mid;
-    }
-    return q;
+    int k = (int)((p + B) * inv_cell);
+    k = max(0, min(k, (1 << kLevels) - 1));
+    while (k > 0 && p < __dadd_rn(__dmul_rn((double)k, cell), -B)) --k;
+    while (k < (1 << kLevels) - 1 && p >= __dadd_rn(__dmul_rn((double)(k + 1), cell), -B)) ++k;
+    return (unsigned int)k;
 }
 
 __global__ void __launch_bounds__(256)
-k_morton(const float4* __restrict__ posw, int n, double B, unsigned long long* __restrict__ keys,
+k_morton(const float4* __restrict__ posw, int n, double B, double cell, double inv_cell, unsigned long long* __restrict__ keys,
          unsigned int* __restrict__ vals, unsigned int* __restrict__ counters)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,7 +82,8 @@ k_morton(const float4* __restrict__ posw, int n, double B, unsigned long long* _
         unsigned long long key = kOutside;
         if (inside)
         {
-            const unsigned int qx = axis_cell((double)p.x, B), qy = axis_cell((double)p.y, B), qz = axis_cell((double)p.z, B);
+            const unsigned int qx = axis_cell((double)p.x, B, cell, inv_cell), qy = axis_cell((double)p.y, B, cell, inv_cell),
+                               qz = axis_cell((double)p.z, B, cell, inv_cell);
             key = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
         }
         keys[i] = key;
@@ -170,58 +168,107 @@ __global__ void __launch_bounds__(256) k_rs_scan_totals(unsigned int* __restrict
     totals[threadIdx.x] = s[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+// Scatter of one tile.  (1) every key gets its rank among the keys of the same digit that precede
+// it in the tile (warp-level match.any per round + running per-warp counters; the order is warp,
+// round, lane = input order, so the sort is stable); (2) the tile is reordered by digit in shared
+// memory; (3) thread t writes tile slot t + 256 k, so keys of one digit leave as contiguous runs
+// (mean run 16 keys = 128 B for uniform digits, far longer in the high passes) instead of 8-byte
+// scattered stores.
+constexpr size_t RS_SCATTER_SMEM = RS_TILE * (sizeof(unsigned long long) + sizeof(unsigned int) + sizeof(unsigned short)) +
+                                   (RS_WARPS + 2) * 256 * sizeof(unsigned int);
+
+__global__ void __launch_bounds__(RS_THREADS, 3)
 k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
              unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
              const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals, int tiles)
 {
-    __shared__ unsigned int wh[RS_WARPS][256];
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(rs_smem);            // tile, input order
+    unsigned int* svals = reinterpret_cast<unsigned int*>(skeys + RS_TILE);
+    unsigned int (*wh)[256] = reinterpret_cast<unsigned int (*)[256]>(svals + RS_TILE);   // [RS_WARPS][256]
+    unsigned int* lbase = &wh[RS_WARPS][0];      // first digit-ordered slot of each digit
+    unsigned int* gbase = lbase + 256;           // global position of digit-ordered slot s of digit d = gbase[d] + s
+    unsigned short* perm = reinterpret_cast<unsigned short*>(gbase + 256);                 // digit-ordered slot -> input slot
+    __shared__ unsigned int warp_tot[RS_WARPS];
+
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
+
+    const int tile_base = blockIdx.x * RS_TILE;
+    const int wbase = warp * (RS_ITEMS * 32);    // warp w owns input slots [512 w, 512 w + 512)
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const int ip = wbase + r * 32 + lane;
+        const bool ok = tile_base + ip < n;
+        skeys[ip] = ok ? keys_in[tile_base + ip] : 0ull;
+        svals[ip] = ok ? vals_in[tile_base + ip] : 0u;
+    }
     __syncthreads();
 
-    const int chunk = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
-    unsigned long long key[RS_ITEMS];
-    unsigned int val[RS_ITEMS];
+    const unsigned int lt = (1u << lane) - 1u;
+    unsigned int packed[RS_ITEMS];               // digit << 16 | rank among the warp's earlier keys of that digit
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
     {
-        const int i = chunk + r * 32 + lane;
-        const bool ok = i < n;
-        key[r] = ok ? keys_in[i] : 0ull;
-        val[r] = ok ? vals_in[i] : 0u;
+        const int ip = wbase + r * 32 + lane;
+        const bool ok = tile_base + ip < n;
         // invalid lanes get a private pseudo-digit so they never match anyone
-        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & 255u) : (256u + lane);
+        const unsigned int d = ok ? ((unsigned int)(skeys[ip] >> shift) & 255u) : (256u + lane);
         const unsigned int peers = __match_any_sync(0xffffffffu, d);
-        if (ok && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+        const unsigned int before = ok ? wh[warp][d] : 0u;
+        __syncwarp();
+        packed[r] = (d << 16) | (before + __popc(peers & lt));
+        if (ok && lane == __ffs(peers) - 1) wh[warp][d] = before + __popc(peers);
         __syncwarp();
     }
     __syncthreads();
     {
+        // thread d: exclusive scan over the warps, then over the digits (block scan of the totals)
         const int d = threadIdx.x;   // RS_THREADS == 256 digits
-        unsigned int run = totals[d] + hist[(size_t)d * tiles + blockIdx.x];
+        unsigned int run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { const unsigned int c = wh[w][d]; wh[w][d] = run; run += c; }
+        unsigned int x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        unsigned int wprefix = 0;
+        for (int w = 0; w < warp; ++w) wprefix += warp_tot[w];
+        const unsigned int first = wprefix + x - run;
+        lbase[d] = first;
+        gbase[d] = totals[d] + hist[(size_t)d * tiles + blockIdx.x] - first;
     }
     __syncthreads();
-    const unsigned int lt = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
     {
-        const int i = chunk + r * 32 + lane;
-        const bool ok = i < n;
-        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & 255u) : (256u + lane);
-        const unsigned int peers = __match_any_sync(0xffffffffu, d);
-        unsigned int pos = 0;
-        if (ok) pos = wh[warp][d] + __popc(peers & lt);
-        __syncwarp();
-        if (ok)
+        const int ip = wbase + r * 32 + lane;
+        if (tile_base + ip < n)
         {
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
-            if (lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+            const unsigned int d = packed[r] >> 16;
+            perm[lbase[d] + wh[warp][d] + (packed[r] & 0xffffu)] = (unsigned short)ip;
         }
-        __syncwarp();
+    }
+    __syncthreads();
+    const int live = min(RS_TILE, n - tile_base);
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k)
+    {
+        const int slot = k * RS_THREADS + threadIdx.x;
+        if (slot < live)
+        {
+            const int ip = perm[slot];
+            const unsigned long long kk = skeys[ip];
+            const unsigned int pos = gbase[(unsigned int)(kk >> shift) & 255u] + slot;
+            keys_out[pos] = kk;
+            vals_out[pos] = svals[ip];
+        }
     }
 }
 
@@ -239,7 +286,7 @@ __device__ __forceinline__ int delta_fn(const unsigned long long* __restrict__ k
 
 __global__ void __launch_bounds__(256)
 k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ counters, int leaf_base,
-         int* __restrict__ child_l, int* __restrict__ child_r, int* __restrict__ prefix, int* __restrict__ parent,
+         int2* __restrict__ child, int* __restrict__ prefix, int* __restrict__ parent,
          unsigned int* __restrict__ flags, int* __restrict__ first_slot)
 {
     const int m = (int)counters[C_INBOUNDS];
@@ -264,8 +311,7 @@ k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __rest
     const int lo = min(i, j), hi = max(i, j);
     const int cl = (lo == gamma) ? leaf_base + gamma : gamma;
     const int cr = (hi == gamma + 1) ? leaf_base + gamma + 1 : gamma + 1;
-    child_l[i] = cl;
-    child_r[i] = cr;
+    child[i] = make_int2(cl, cr);
     prefix[i] = dnode;
     first_slot[i] = lo;
     parent[cl] = i;
@@ -279,10 +325,10 @@ k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __rest
 // which accumulates the centre of mass in fp32 and overflows for large total mass -- fp64 here).
 // One thread per leaf climbs; the second arrival at a node combines (left + right).
 // ------------------------------------------------------------------------------------------------
+// Node sums are 32-byte records {w, w x, w y, w z} (one sector per node).
 __device__ __forceinline__ void load_node(int id, int leaf_base, const float4* __restrict__ posw,
-                                          const unsigned int* __restrict__ order, const double* nw,
-                                          const double* ns, size_t plane, double& w, double& sx,
-                                          double& sy, double& sz)
+                                          const unsigned int* __restrict__ order, const double* nsum,
+                                          double& w, double& sx, double& sy, double& sz)
 {
     if (id >= leaf_base)
     {
@@ -293,16 +339,16 @@ __device__ __forceinline__ void load_node(int id, int leaf_base, const float4* _
     else
     {
         // written by another SM earlier in this kernel: read through L2, never a stale L1 line
-        w = __ldcg(nw + id);
-        sx = __ldcg(ns + id); sy = __ldcg(ns + plane + id); sz = __ldcg(ns + 2 * plane + id);
+        const double2* rec = reinterpret_cast<const double2*>(nsum + 4 * (size_t)id);
+        const double2 a = __ldcg(rec), b = __ldcg(rec + 1);
+        w = a.x; sx = a.y; sy = b.x; sz = b.y;
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ order,
-            const unsigned int* __restrict__ counters, int leaf_base, const int* __restrict__ child_l,
-            const int* __restrict__ child_r, const int* __restrict__ parent, unsigned int* __restrict__ flags,
-            double* nw, double* ns, size_t plane)
+            const unsigned int* __restrict__ counters, int leaf_base, const int2* __restrict__ child,
+            const int* __restrict__ parent, unsigned int* __restrict__ flags, double* nsum)
 {
     const int m = (int)counters[C_INBOUNDS];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,16 +356,18 @@ k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ or
     int node = parent[leaf_base + j];
     while (node != kEnd)
     {
-        __threadfence();
-        if (atomicAdd(&flags[node], 1u) == 0u) return;   // first arrival: the sibling subtree is not done
-        __threadfence();
+        // One acq_rel atomic instead of fence + atomic + fence: the release half publishes the record this
+        // thread stored one level below, the acquire half orders the sibling's record before the loads.
+        unsigned int arrived;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(arrived) : "l"(flags + node), "r"(1u) : "memory");
+        if (arrived == 0u) return;                       // first arrival: the sibling subtree is not done
+        const int2 c = child[node];
         double wl, lx, ly, lz, wr, rx, ry, rz;
-        load_node(child_l[node], leaf_base, posw, order, nw, ns, plane, wl, lx, ly, lz);
-        load_node(child_r[node], leaf_base, posw, order, nw, ns, plane, wr, rx, ry, rz);
-        nw[node] = wl + wr;
-        ns[node] = lx + rx;
-        ns[plane + node] = ly + ry;
-        ns[2 * plane + node] = lz + rz;
+        load_node(c.x, leaf_base, posw, order, nsum, wl, lx, ly, lz);
+        load_node(c.y, leaf_base, posw, order, nsum, wr, rx, ry, rz);
+        double2* rec = reinterpret_cast<double2*>(nsum + 4 * (size_t)node);
+        rec[0] = make_double2(wl + wr, lx + rx);
+        rec[1] = make_double2(ly + ry, lz + rz);
         node = parent[node];
     }
 }
@@ -392,7 +440,7 @@ k_scan_apply(const unsigned int* __restrict__ in, int n, const unsigned int* __r
 }
 
 __global__ void __launch_bounds__(256)
-k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int* __restrict__ child_l,
+k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int2* __restrict__ child,
        const int* __restrict__ prefix, const int* __restrict__ parent, const int* __restrict__ first_slot,
        const unsigned int* __restrict__ pref, int* __restrict__ rank)
 {
@@ -406,7 +454,7 @@ k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int* __r
         for (;;)
         {
             const int p = parent[v];
-            if (p == kEnd || child_l[p] != v) break;
+            if (p == kEnd || child[p].x != v) break;
             if (owns_cell(p, prefix, parent)) ++above;
             v = p;
         }
@@ -416,18 +464,18 @@ k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int* __r
 }
 
 // The record after the subtree of `id` in pre-order (kEnd if none).
-__device__ __forceinline__ int after_subtree(int id, int leaf_base, const int* __restrict__ child_l,
-                                             const int* __restrict__ child_r, const int* __restrict__ prefix,
-                                             const int* __restrict__ parent)
+__device__ __forceinline__ int after_subtree(int id, int leaf_base, const int2* __restrict__ child,
+                                             const int* __restrict__ prefix, const int* __restrict__ parent)
 {
     for (;;)
     {
         const int p = parent[id];
         if (p == kEnd) return kEnd;
-        if (child_l[p] == id)
+        const int2 c = child[p];
+        if (c.x == id)
         {
-            int r = child_r[p];
-            while (r < leaf_base && !owns_cell(r, prefix, parent)) r = child_l[r];
+            int r = c.y;
+            while (r < leaf_base && !owns_cell(r, prefix, parent)) r = child[r].x;
             return r;
         }
         id = p;
@@ -439,9 +487,9 @@ __device__ __forceinline__ int after_subtree(int id, int leaf_base, const int* _
 // evaluated), owning nodes (width / theta)^2.
 __global__ void __launch_bounds__(256)
 k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ counters,
-           int leaf_base, const int* __restrict__ child_l, const int* __restrict__ child_r,
-           const int* __restrict__ prefix, const int* __restrict__ parent, const double* __restrict__ nw,
-           const double* __restrict__ ns, size_t plane, float root_width, float inv_theta,
+           int leaf_base, const int2* __restrict__ child,
+           const int* __restrict__ prefix, const int* __restrict__ parent, const double* __restrict__ nsum,
+           float root_width, float inv_theta,
            const int* __restrict__ rank, float4* __restrict__ nodes)
 {
     const int m = (int)counters[C_INBOUNDS];
@@ -458,14 +506,15 @@ k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ ord
     if (t < m - 1 && owns_cell(t, prefix, parent))
     {
         const int r = rank[t];
-        const int nxt = after_subtree(t, leaf_base, child_l, child_r, prefix, parent);
+        const int nxt = after_subtree(t, leaf_base, child, prefix, parent);
         const int skip = nxt == kEnd ? total : rank[nxt];
-        const double w = nw[t];
+        const double2* rec = reinterpret_cast<const double2*>(nsum + 4 * (size_t)t);
+        const double2 s0 = rec[0], s1 = rec[1];
+        const double w = s0.x;
         const double inv = w != 0.0 ? 1.0 / w : 0.0;
         const float width = ldexpf(root_width, -level_of(prefix[t]));
         const float lim = width * inv_theta;
-        nodes[2 * (size_t)r] = make_float4((float)(ns[t] * inv), (float)(ns[plane + t] * inv), (float)(ns[2 * plane + t] * inv),
-                                           (float)w * kPreScale);
+        nodes[2 * (size_t)r] = make_float4((float)(s0.y * inv), (float)(s1.x * inv), (float)(s1.y * inv), (float)w * kPreScale);
         nodes[2 * (size_t)r + 1] = make_float4(lim * lim, __int_as_float(skip), __int_as_float(-1), 0.f);
     }
 }
@@ -479,12 +528,15 @@ k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ ord
 // Interaction: same law as all-pairs, a += G M (c - p) / (|d| (d^2 + S)); the self term and
 // coincident bodies vanish through the epsilon (see allpairs.cuh).
 // ------------------------------------------------------------------------------------------------
-template <bool STATS>
+template <bool STATS, int GROUP>
 __global__ void __launch_bounds__(256)
 k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ tlist,
        int ntargets, const unsigned int* __restrict__ counters, const float4* __restrict__ nodes,
        int first, int count, float sc, double* __restrict__ acc, unsigned long long* __restrict__ stats)
 {
+    // GROUP consecutive lanes share one traversal pointer (32 = the whole warp, the default).  Smaller
+    // groups walk a smaller union of subtrees, but the warp runs until its slowest group is done and the
+    // vote costs more: measured at 16 M bodies 37.6 ms (32) / 42.0 ms (16) / 40.9 ms (8).
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < ntargets;
     unsigned int body = 0;
@@ -495,15 +547,20 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
         p = posw[body];
     }
     const int total = (int)counters[C_TOTAL];
+    const unsigned int gmask = GROUP == 32 ? 0xffffffffu : ((GROUP == 16 ? 0xffffu : 0xffu) << (threadIdx.x & (32 - GROUP) & 31));
     int cur = 0;
-    int parked = 0;                      // the lane is idle while cur < parked
+    int parked = valid ? 0 : 0x7fffffff;   // the lane is idle while cur < parked; lanes without a target never wake
     float ax = 0.f, ay = 0.f, az = 0.f;
     unsigned int n_cells = 0, n_leaves = 0, n_visits = 0;
-    while (cur < total)
+    for (;;)
     {
-        const float4 a = nodes[2 * (size_t)cur];
-        const float4 b = nodes[2 * (size_t)cur + 1];
-        const bool active = valid && cur >= parked;
+        const bool live = cur < total;
+        if (GROUP == 32) { if (!live) break; }
+        else if (!__any_sync(0xffffffffu, live)) break;
+        const size_t rec = 2 * (size_t)(live ? cur : 0);
+        const float4 a = nodes[rec];
+        const float2 b = *reinterpret_cast<const float2*>(nodes + rec + 1);
+        const bool active = live && cur >= parked;
         const float dx = a.x - p.x, dy = a.y - p.y, dz = a.z - p.z;
         float d2 = dx * dx;
         d2 = fmaf(dy, dy, d2);
@@ -523,10 +580,16 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
         if (STATS && active)
         {
             ++n_visits;
-            if (accept) { if (thr < 0.f) n_leaves += ((unsigned int)__float_as_int(b.z) != body); else ++n_cells; }
+            if (accept)
+            {
+                if (thr < 0.f) n_leaves += ((unsigned int)__float_as_int(nodes[rec + 1].z) != body);
+                else ++n_cells;
+            }
         }
-        const bool open = __any_sync(0xffffffffu, active && !accept);
-        cur = open ? cur + 1 : skip;
+        bool open;
+        if (GROUP == 32) open = __any_sync(0xffffffffu, active && !accept);
+        else open = (__ballot_sync(0xffffffffu, active && !accept) & gmask) != 0u;
+        if (live) cur = open ? cur + 1 : skip;
     }
     if (valid)
     {
@@ -628,7 +691,7 @@ void tree_release(nb_sim* h)
     TreeBuffers& t = h->tree;
     for (int k = 0; k < 2; ++k) { cudaFree(t.keys[k]); cudaFree(t.vals[k]); t.keys[k] = nullptr; t.vals[k] = nullptr; }
     cudaFree(t.hist); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
-    cudaFree(t.range); cudaFree(t.flags); cudaFree(t.nmass); cudaFree(t.ncom); cudaFree(t.walk_a);
+    cudaFree(t.range); cudaFree(t.flags); cudaFree(t.nsum); cudaFree(t.walk_a);
     cudaFree(t.walk_b); cudaFree(t.stats); cudaFree(t.cnt); cudaFree(t.pref); cudaFree(t.rank); cudaFree(t.tlist);
     t = TreeBuffers();
 }
@@ -648,7 +711,7 @@ int tree_reserve(nb_sim* h)
     t.hist_words = 256 * tiles + 256 + tiles + 16;
     NB_CUDA(cudaMalloc(&t.hist, t.hist_words * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.counters, C_WORDS * sizeof(unsigned int)));
-    NB_CUDA(cudaMalloc(&t.child, 2 * n * sizeof(int)));
+    NB_CUDA(cudaMalloc(&t.child, n * sizeof(int2)));
     NB_CUDA(cudaMalloc(&t.parent, 2 * n * sizeof(int)));
     NB_CUDA(cudaMalloc(&t.prefix, n * sizeof(int)));
     NB_CUDA(cudaMalloc(&t.range, n * sizeof(int)));                   // first slot of every node's range
@@ -657,8 +720,7 @@ int tree_reserve(nb_sim* h)
     NB_CUDA(cudaMalloc(&t.rank, 2 * n * sizeof(int)));
     NB_CUDA(cudaMalloc(&t.tlist, n * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.flags, n * sizeof(unsigned int)));
-    NB_CUDA(cudaMalloc(&t.nmass, n * sizeof(double)));
-    NB_CUDA(cudaMalloc(&t.ncom, 3 * n * sizeof(double)));
+    NB_CUDA(cudaMalloc(&t.nsum, 4 * n * sizeof(double)));
     NB_CUDA(cudaMalloc(&t.walk_a, 4 * n * sizeof(float4)));           // 2n records x 32 B
     NB_CUDA(cudaMalloc(&t.stats, 3 * sizeof(unsigned long long)));
     NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), h->stream));
@@ -675,10 +737,17 @@ int tree_build(nb_sim* h)
     cudaStream_t st = h->stream;
 
     NB_CUDA(cudaMemsetAsync(t.counters, 0, C_WORDS * sizeof(unsigned int), st));
-    k_morton<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, t.keys[0], t.vals[0], t.counters);
+    const double cell = std::ldexp((double)h->cfg.bounds, 1 - kLevels);      // 2B / 2^21, exact
+    k_morton<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, cell, 1.0 / cell, t.keys[0], t.vals[0], t.counters);
     ++h->last_launches;
 
     unsigned int* totals = t.hist + (size_t)256 * tiles;
+    static bool smem_opt_in = false;
+    if (!smem_opt_in)
+    {
+        NB_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+        smem_opt_in = true;
+    }
     int src = 0;
     for (int pass = 0; pass < 8; ++pass)
     {
@@ -686,8 +755,8 @@ int tree_build(nb_sim* h)
         k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], n, shift, t.hist, tiles);
         k_rs_scan_rows<<<256, 256, 0, st>>>(t.hist, tiles, totals);
         k_rs_scan_totals<<<1, 256, 0, st>>>(totals);
-        k_rs_scatter<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, shift,
-                                                  t.hist, totals, tiles);
+        k_rs_scatter<<<tiles, RS_THREADS, RS_SCATTER_SMEM, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, shift,
+                                                                t.hist, totals, tiles);
         h->last_launches += 4;
         src ^= 1;
     }
@@ -695,12 +764,8 @@ int tree_build(nb_sim* h)
     NB_CUDA(cudaGetLastError());
 
     const int leaf_base = n;
-    int* child_l = t.child;
-    int* child_r = t.child + n;
-    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, child_l, child_r, t.prefix, t.parent, t.flags,
-                                                t.range);
-    k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, child_l, child_r, t.parent,
-                                                   t.flags, t.nmass, t.ncom, (size_t)n);
+    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range);
+    k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.parent, t.flags, t.nsum);
     // pre-order ranks: count owning nodes per first slot, exclusive scan, rank, then the records
     {
         const int words = n + 1;
@@ -712,12 +777,11 @@ int tree_build(nb_sim* h)
         k_block_sums<<<sblocks, 256, 0, st>>>(t.cnt, words, sums);
         k_rs_scan_rows<<<1, 256, 0, st>>>(sums, sblocks, total);
         k_scan_apply<<<sblocks, 256, 0, st>>>(t.cnt, words, sums, t.pref);
-        k_rank<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, n, leaf_base, child_l, t.prefix, t.parent, t.range, t.pref, t.rank);
+        k_rank<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, n, leaf_base, t.child, t.prefix, t.parent, t.range, t.pref, t.rank);
         h->last_launches += 5;
     }
-    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, child_l, child_r, t.prefix,
-                                                  t.parent, t.nmass, t.ncom, (size_t)n, 2.0f * h->cfg.bounds,
-                                                  1.0f / h->cfg.theta, t.rank, t.walk_a);
+    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.prefix,
+                                                  t.parent, t.nsum, 2.0f * h->cfg.bounds, 1.0f / h->cfg.theta, t.rank, t.walk_a);
     h->last_launches += 3;
     NB_CUDA(cudaGetLastError());
     t.built = true;
@@ -750,17 +814,21 @@ int tree_walk(nb_sim* h)
         ntargets = (int)h->count;
     }
     const float sc = (float)(h->cfg.softening * (double)kPreScale);
+    const int blocks = blocks_for(ntargets, 256);
+#define NB_WALK(STATS, GROUP)                                                                                            \
+    k_walk<STATS, GROUP><<<blocks, 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, \
+                                                 (int)h->count, sc, h->acc, t.stats)
+    // kernel_variant 1 / 2: 16- / 8-lane groups (measured slower, kept for the record: DESIGN.md K7)
+    const int group = h->cfg.kernel_variant == 1 ? 16 : (h->cfg.kernel_variant == 2 ? 8 : 32);
     if (g_walk_stats)
     {
         NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), st));
-        k_walk<true><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a,
-                                                              (int)h->first, (int)h->count, sc, h->acc, t.stats);
+        NB_WALK(true, 32);
     }
-    else
-    {
-        k_walk<false><<<blocks_for(ntargets, 256), 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a,
-                                                               (int)h->first, (int)h->count, sc, h->acc, t.stats);
-    }
+    else if (group == 32) NB_WALK(false, 32);
+    else if (group == 16) NB_WALK(false, 16);
+    else NB_WALK(false, 8);
+#undef NB_WALK
     ++h->last_launches;
     NB_CUDA(cudaGetLastError());
     return NB_OK;
@@ -803,26 +871,27 @@ int nb_get_tree(nb_handle h, int32_t* left, int32_t* right, int32_t* prefix_bits
     if (k == 0) return NB_OK;
     const size_t n = h->n;
     const int leaf_base = (int)n;
-    std::vector<int> tmp(k);
-    for (int side = 0; side < 2; ++side)
+    if (left || right)
     {
-        int32_t* dst = side == 0 ? left : right;
-        if (!dst) continue;
-        NB_CUDA(cudaMemcpy(tmp.data(), h->tree.child + side * n, k * sizeof(int), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < k; ++i) dst[i] = tmp[i] >= leaf_base ? ~(tmp[i] - leaf_base) : tmp[i];
+        std::vector<int2> tmp(k);
+        NB_CUDA(cudaMemcpy(tmp.data(), h->tree.child, k * sizeof(int2), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < k; ++i)
+        {
+            if (left) left[i] = tmp[i].x >= leaf_base ? ~(tmp[i].x - leaf_base) : tmp[i].x;
+            if (right) right[i] = tmp[i].y >= leaf_base ? ~(tmp[i].y - leaf_base) : tmp[i].y;
+        }
     }
     if (prefix_bits) NB_CUDA(cudaMemcpy(prefix_bits, h->tree.prefix, k * sizeof(int), cudaMemcpyDeviceToHost));
     if (mass || com3)
     {
-        std::vector<double> w(k), s(3 * k);
-        NB_CUDA(cudaMemcpy(w.data(), h->tree.nmass, k * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int c = 0; c < 3; ++c)
-            NB_CUDA(cudaMemcpy(s.data() + c * k, h->tree.ncom + c * n, k * sizeof(double), cudaMemcpyDeviceToHost));
+        std::vector<double> s4(4 * k);
+        NB_CUDA(cudaMemcpy(s4.data(), h->tree.nsum, 4 * k * sizeof(double), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < k; ++i)
         {
-            if (mass) mass[i] = w[i] / h->cfg.G;
+            const double w = s4[4 * i];
+            if (mass) mass[i] = w / h->cfg.G;
             if (com3)
-                for (int c = 0; c < 3; ++c) com3[3 * i + c] = (float)(w[i] != 0.0 ? s[c * k + i] / w[i] : 0.0);
+                for (int c = 0; c < 3; ++c) com3[3 * i + c] = (float)(w != 0.0 ? s4[4 * i + 1 + c] / w : 0.0);
         }
     }
     return NB_OK;
