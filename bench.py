@@ -127,9 +127,7 @@ def cpu_sample(p, mode, seconds, theta=0.5):
     n = len(p)
     if mode == "allpairs":
         if ref.available():
-            w = 1
-            while w * 2 <= min(ref.lib().ref_hardware_workers(), 512):
-                w *= 2
+            w = max(1, min(ref.lib().ref_hardware_workers(), 512))     # the reference pool's own size: hardware_concurrency() - 1
             count = w * 2
             secs, used, _ = ref.bruteforce_block(p, 0, count, workers=w)       # calibration + warm-up
             rate = count * (n - 1) / secs

@@ -266,8 +266,12 @@ extern "C"
         std::vector<Particle> v = ToVector(aos, n);
         BruteForceCPU* sim = BruteSim();
         const uint32_t spawned = g_bruteSpawned;
-        uint32_t w = PickWorkers(workers, spawned, count);
-        while (w > 1 && (first % (count / w)) != 0) w /= 2;
+        // any worker count that divides the block (the pool itself has no power-of-two constraint):
+        // the largest w <= min(request, spawned) with count % w == 0 and the block aligned to count / w
+        uint32_t w = spawned;
+        if (workers > 0 && static_cast<uint32_t>(workers) < w) w = workers;
+        if (w < 1) w = 1;
+        while (w > 1 && ((count % w) != 0 || (first % (count / w)) != 0)) --w;
         if (workersUsed) *workersUsed = static_cast<int>(w);
         sim->Init(v);
         for (size_t k = 0; k < count; ++k) v[first + k].Forces = Vec3d();

@@ -326,3 +326,29 @@ def test_sampled_energy_estimator(pkg):
     # and it estimates the whole: within the sampling noise of 512 bodies of a bimodal mass spectrum
     assert abs(pe8 - pe) < 0.25 * abs(pe)
     sim.close()
+
+
+def test_energy_drift_at_65536_bodies_tracks_the_reference(pkg):
+    """The same comparison at 16x the bodies (tests/golden/make_golden_drift64k.py: the reference's
+    Barnes-Hut CPU path, 1000 steps, ~10 minutes on 4 workers): total mass and drift are several times
+    larger than at 4096 bodies, so this is the sharper check that the GPU path integrates the same
+    system.  Energies every 250 steps, exact pair sum on both sides."""
+    g = load_golden("energy_drift_n65536.npz")
+    n = int(g["n"])
+    scene = pkg.seed_collision_host(n, 42, 1.0, separation=float(g["separation"]), approach_speed=float(g["approach"]))
+    sim = bh(pkg, theta=float(g["theta"]))
+    sim.init(scene)
+    ke0, pe0 = sim.energy()
+    assert abs(ke0 - g["energies"][0, 0]) < 1e-9 * abs(ke0) and abs(pe0 - g["energies"][0, 1]) < 1e-6 * abs(pe0)
+    e0 = ke0 + pe0
+    drift = [0.0]
+    for _ in range(len(g["drift"]) - 1):
+        sim.step(float(g["dt"]), int(g["every"]))
+        ke, pe = sim.energy()
+        drift.append(abs(ke + pe - e0) / abs(e0))
+    drift = np.array(drift)
+    print("energy drift ours      (N=65536):", drift)
+    print("energy drift reference (N=65536):", g["drift"])
+    assert drift[-1] <= 2.0 * g["drift"][-1] and drift.max() <= 2.0 * g["drift"].max()
+    assert np.all(np.abs(drift[1:] - g["drift"][1:]) <= 0.25 * g["drift"][1:] + 1e-5)
+    sim.close()
