@@ -405,7 +405,7 @@ def main():
             line["roofline"] = {
                 "bound": "fp32", "kernel": "k_walk (warp-cooperative stackless traversal)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": "measured live by nb_probe_fp32_peak; the walk is latency-bound (dependent node loads), see DESIGN.md",
+                "peak_source": "measured live by nb_probe_fp32_peak; the walk is issue-bound (28 instructions per node visit, ~50% of lane slots do an interaction), see DESIGN.md K7",
                 "flops_per_interaction": FLOPS_PER_INTERACTION, "interactions_per_launch": evals_launch,
                 "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / total_ms,
                 "node_visits_per_launch": float(mine["visits"]),
