@@ -53,6 +53,13 @@ WORKLOADS = {
 }
 COLLISION = dict(separation=2000.0, approach_speed=2e16)     # the scene of tests/golden/energy_drift_n4096.npz
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+# `ncu --set full` captures (1 GPU); only quoted for the exact workload they were taken on.
+NCU_TRAFFIC = {
+    ("allpairs_1m", 1): (46.866432e6 + 281.826304e6, "profiles/r1_allpairs_fold2_ncu_full.txt"),
+    ("bh_16m", 1): (2.639446e9 + 1.037880e9, "profiles/r1_bh_16m_ncu_full.txt"),
+}
+
 FLOPS_PER_INTERACTION = 20   # 3 sub, 5 d^2, 1 add S, 1 sqrt, 1 div, 3 div, 3 mul, 3 add
 
 
@@ -413,6 +420,8 @@ def main():
                           "achieved": build_bytes / (build_ms * 1e-3) * 1e-9, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                           "frac": build_bytes / (build_ms * 1e-3) * 1e-9 / pk.get("hbm_gbs", 6546.9)},
             }
+        if (args.workload, world) in NCU_TRAFFIC and args.variant == 0:
+            line["roofline"]["traffic"], line["roofline"]["traffic_source"] = NCU_TRAFFIC[(args.workload, world)]
         if e2e is None and not args.no_e2e:
             line["e2e"] = {"value": per_step * args.steps / e2e_s, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                            "ms_per_step": e2e_s * 1e3 / args.steps,

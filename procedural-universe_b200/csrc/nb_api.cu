@@ -28,7 +28,7 @@ static int free_state(nb_sim* h)
     cudaFree(h->p2p_flags); h->p2p_flags = nullptr;
     cudaFree(h->vel); h->vel = nullptr;
     cudaFree(h->mass); h->mass = nullptr;
-    cudaFree(h->acc); h->acc = nullptr;
+    cudaFree(h->acc_base); h->acc_base = nullptr; h->acc = nullptr; h->acc_cur = 0; h->acc_two = false;
     cudaFree(h->acc_part); h->acc_part = nullptr;
     h->acc_part_splits = 0;
     tree_release(h);
@@ -122,7 +122,10 @@ int launch_allpairs(nb_sim* h)
 
 // `timed`: bracket the dominant kernel (all-pairs kernel / tree walk) with ev[2], ev[3] and the
 // tree build with ev[4], ev[2].
-static int compute_forces(nb_sim* h, bool timed)
+// `balanced`: Barnes-Hut inside nb_step with peer memory attached -- every rank walks an interleaved
+// share of ALL targets and stores into the owners' arrays; the exchange that follows makes sure this
+// rank's own accelerations are complete before the kick-drift reads them.
+static int compute_forces(nb_sim* h, bool timed, bool balanced = false)
 {
     if (timed) NB_CUDA(cudaEventRecord(h->ev[4], h->stream));
     if (h->cfg.mode == NB_MODE_ALLPAIRS)
@@ -134,9 +137,10 @@ static int compute_forces(nb_sim* h, bool timed)
     {
         NB_CHECK(tree_build(h));
         if (timed) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        NB_CHECK(tree_walk(h));
+        NB_CHECK(tree_walk(h, balanced));
     }
     if (timed) NB_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    if (balanced && h->cfg.mode == NB_MODE_BARNESHUT) NB_CHECK(p2p_acc_exchange(h));
     return NB_OK;
 }
 
@@ -156,7 +160,9 @@ static int set_bodies(nb_sim* h, size_t n)
         h->posw_cur = 0;
         NB_CUDA(cudaMalloc(&h->vel, 3 * h->count * sizeof(double)));
         NB_CUDA(cudaMalloc(&h->mass, h->count * sizeof(double)));
-        NB_CUDA(cudaMalloc(&h->acc, 3 * h->count * sizeof(double)));
+        NB_CUDA(cudaMalloc(&h->acc_base, 3 * h->count * sizeof(double)));
+        h->acc = h->acc_base;
+        h->acc_cur = 0;
         NB_CUDA(cudaMemsetAsync(h->acc, 0, 3 * h->count * sizeof(double), h->stream));
         if (h->cfg.mode == NB_MODE_BARNESHUT) NB_CHECK(tree_reserve(h));
     }
@@ -341,7 +347,7 @@ int nb_step(nb_handle h, float dt, int nsteps)
                    "world > 1 without nb_comm_init: call nb_mark_exchanged after exchanging positions");
         const bool last = (s == nsteps - 1);
         if (h->p2p_attached) NB_CHECK(p2p_wait(h));          // every peer's positions of the last step are in
-        NB_CHECK(compute_forces(h, last));
+        NB_CHECK(compute_forces(h, last, h->p2p_attached && h->cfg.world > 1 && h->cfg.mode == NB_MODE_BARNESHUT));
         h->acc_valid = false;
         h->forces_from_last_step = true;
         if (h->p2p_attached)

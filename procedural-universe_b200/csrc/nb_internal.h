@@ -56,6 +56,7 @@ struct TreeBuffers
     unsigned int* cnt = nullptr;    // [n+1] owning nodes per first slot
     unsigned int* pref = nullptr;   // [n+1] exclusive scan of cnt
     int* rank = nullptr;            // [2n]  pre-order rank of every traversal record
+    unsigned short* meta = nullptr; // [n-1] octree level of an internal node | 0x100 if it owns octree cells
     unsigned int* tlist = nullptr;  // [n]   owned targets in Morton order (world > 1)
     int sort_bits_done = 0;
     int cur = 0;                    // which ping-pong half holds the sorted result
@@ -63,6 +64,18 @@ struct TreeBuffers
     bool built = false;
 };
 
+}  // namespace nb
+
+namespace nb
+{
+// Where a balanced walk stores accelerations: rank r's acc[3][count_r] planes and its first body.
+struct AccTable
+{
+    double* acc[NB_MAX_PEERS];        // rank r's two acc buffers, [2][3][count_r]
+    int first[NB_MAX_PEERS + 1];      // first[r] = r * n / world; first[world] = n
+    int world, rank;
+    int parity;                       // which of the two buffers this step writes
+};
 }  // namespace nb
 
 struct nb_sim
@@ -81,7 +94,10 @@ struct nb_sim
     int posw_cur = 0;
     double* vel = nullptr;       // [3][count] velocity planes of owned bodies
     double* mass = nullptr;      // [count]
-    double* acc = nullptr;       // [3][count] accelerations of the last force evaluation
+    double* acc = nullptr;       // [3][count] accelerations of the last force evaluation (== acc_base + acc_cur * 3 * count)
+    double* acc_base = nullptr;  // the allocation: one buffer, or two once peer memory is prepared (p2p.cu)
+    int acc_cur = 0;
+    bool acc_two = false;
     double* acc_part = nullptr;  // [splits][3][count] all-pairs partial sums
     size_t acc_part_splits = 0;
 
@@ -108,9 +124,11 @@ struct nb_sim
     bool p2p_attached = false;
     bool p2p_ipc = false;
     unsigned int p2p_step = 0;
-    unsigned int* p2p_flags = nullptr;            // [NB_MAX_PEERS] step counters raised by the peers
+    unsigned int p2p_acc_step = 0;
+    unsigned int* p2p_flags = nullptr;            // [2][NB_MAX_PEERS] step counters raised by the peers: positions, accelerations
     void* peer_posw[2][NB_MAX_PEERS] = {};
     void* peer_flags[NB_MAX_PEERS] = {};
+    void* peer_acc[NB_MAX_PEERS] = {};            // every rank's acc[3][count] (balanced Barnes-Hut walk)
 };
 
 namespace nb
@@ -127,7 +145,7 @@ int choose_allpairs_config(nb_sim* h);
 int tree_reserve(nb_sim* h);
 void tree_release(nb_sim* h);
 int tree_build(nb_sim* h);
-int tree_walk(nb_sim* h);
+int tree_walk(nb_sim* h, bool balanced = false);
 
 // nccl_dl.cpp
 int comm_unique_id(uint8_t id[128]);
@@ -139,6 +157,9 @@ void comm_destroy(nb_sim* h);
 int p2p_prepare(nb_sim* h);
 int p2p_wait(nb_sim* h);
 int p2p_kick_drift_push(nb_sim* h, float dt);
+struct AccTable;
+int p2p_acc_table(const nb_sim* h, AccTable* out);
+int p2p_acc_exchange(nb_sim* h);
 void p2p_release(nb_sim* h);
 
 // seed_host.cpp / seed_device.cu

@@ -71,18 +71,21 @@ k_kick_drift_push(PeerTable pt, int cur, int first, int count, double* __restric
     }
 }
 
-// Raised after the push kernel has completed (stream order): my stores of `step` are out.
-__global__ void k_signal(PeerTable pt, unsigned int step)
+// Raised after the producing kernel has completed (stream order): my stores of `step` are out.
+// `slot` selects the counter row: 0 = positions (after the push), NB_MAX_PEERS = accelerations (after a
+// balanced walk).
+__global__ void k_signal(PeerTable pt, unsigned int step, int slot)
 {
     const int r = threadIdx.x;
     if (r < pt.world)
     {
         __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[r] + pt.rank), "r"(step) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[r] + slot + pt.rank), "r"(step) : "memory");
     }
 }
 
-// Head of the next force pass: every peer has pushed its positions of `step`.
+// Every peer has raised its counter to `step` (positions: head of the next force pass; accelerations:
+// before the kick-drift).
 __global__ void k_wait(const unsigned int* my_flags, int world, unsigned int step)
 {
     const int r = threadIdx.x;
@@ -103,11 +106,27 @@ int p2p_prepare(nb_sim* h)
         NB_CUDA(cudaMalloc(&h->posw_buf[1], h->n * sizeof(float4)));
         NB_CUDA(cudaMemcpyAsync(h->posw_buf[1], h->posw_buf[0], h->n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
     }
+    if (!h->acc_two)
+    {
+        // Two acceleration buffers: a balanced walk of step s stores into buffer s & 1 of every owner while
+        // the owner may still be reading step s-1's (Forces write-back after its kick-drift).
+        double* two = nullptr;
+        const size_t one = 3 * h->count * sizeof(double);
+        NB_CUDA(cudaMalloc(&two, 2 * one));
+        NB_CUDA(cudaMemcpyAsync(two, h->acc, one, cudaMemcpyDeviceToDevice, h->stream));
+        NB_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned char*>(two) + one, 0, one, h->stream));
+        NB_CUDA(cudaStreamSynchronize(h->stream));
+        cudaFree(h->acc_base);
+        h->acc_base = two;
+        h->acc = two;
+        h->acc_cur = 0;
+        h->acc_two = true;
+    }
     if (h->p2p_flags == nullptr)
     {
-        NB_CUDA(cudaMalloc(&h->p2p_flags, NB_MAX_PEERS * sizeof(unsigned int)));
+        NB_CUDA(cudaMalloc(&h->p2p_flags, 2 * NB_MAX_PEERS * sizeof(unsigned int)));
     }
-    NB_CUDA(cudaMemsetAsync(h->p2p_flags, 0, NB_MAX_PEERS * sizeof(unsigned int), h->stream));
+    NB_CUDA(cudaMemsetAsync(h->p2p_flags, 0, 2 * NB_MAX_PEERS * sizeof(unsigned int), h->stream));
     NB_CUDA(cudaStreamSynchronize(h->stream));
     return NB_OK;
 }
@@ -146,11 +165,42 @@ int p2p_kick_drift_push(nb_sim* h, float dt)
                                                      h->cfg.position_scale);
     NB_CUDA(cudaGetLastError());
     ++h->p2p_step;
-    k_signal<<<1, 32, 0, h->stream>>>(pt, h->p2p_step);
+    k_signal<<<1, 32, 0, h->stream>>>(pt, h->p2p_step, 0);
     NB_CUDA(cudaGetLastError());
     h->last_launches += 2;
     h->posw_cur ^= 1;
     h->posw = h->posw_buf[h->posw_cur];
+    return NB_OK;
+}
+
+int p2p_acc_table(const nb_sim* h, AccTable* out)
+{
+    std::memset(out, 0, sizeof(*out));
+    out->world = h->cfg.world;
+    out->rank = h->cfg.rank;
+    for (int r = 0; r < h->cfg.world; ++r)
+    {
+        NB_REQUIRE(h->peer_acc[r] != nullptr, NB_ERR_STATE, "peer acceleration arrays are not attached");
+        out->acc[r] = static_cast<double*>(h->peer_acc[r]);
+        out->first[r] = (int)((size_t)r * h->n / (size_t)h->cfg.world);
+    }
+    out->first[h->cfg.world] = (int)h->n;
+    out->parity = (int)((h->p2p_acc_step + 1u) & 1u);     // the step p2p_acc_exchange is about to count
+    return NB_OK;
+}
+
+// After a balanced walk: tell every rank that my share of ITS accelerations is stored, then wait until
+// every rank has said the same about mine.
+int p2p_acc_exchange(nb_sim* h)
+{
+    const PeerTable pt = make_table(h);
+    ++h->p2p_acc_step;
+    h->acc_cur = (int)(h->p2p_acc_step & 1u);             // what the walk just filled (p2p_acc_table's parity)
+    h->acc = h->acc_base + (size_t)h->acc_cur * 3 * h->count;
+    k_signal<<<1, 32, 0, h->stream>>>(pt, h->p2p_acc_step, NB_MAX_PEERS);
+    k_wait<<<1, 32, 0, h->stream>>>(h->p2p_flags + NB_MAX_PEERS, h->cfg.world, h->p2p_acc_step);
+    NB_CUDA(cudaGetLastError());
+    h->last_launches += 2;
     return NB_OK;
 }
 
@@ -163,12 +213,15 @@ void p2p_release(nb_sim* h)
             for (int b = 0; b < 2; ++b)
                 if (h->peer_posw[b][r]) cudaIpcCloseMemHandle(h->peer_posw[b][r]);
             if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+            if (h->peer_acc[r]) cudaIpcCloseMemHandle(h->peer_acc[r]);
         }
     std::memset(h->peer_posw, 0, sizeof(h->peer_posw));
     std::memset(h->peer_flags, 0, sizeof(h->peer_flags));
+    std::memset(h->peer_acc, 0, sizeof(h->peer_acc));
     h->p2p_attached = false;
     h->p2p_ipc = false;
     h->p2p_step = 0;
+    h->p2p_acc_step = 0;
 }
 
 }  // namespace nb
@@ -184,10 +237,11 @@ int nb_p2p_export(nb_handle h, uint8_t handles[NB_P2P_HANDLE_BYTES])
     NB_REQUIRE(h->cfg.world <= NB_MAX_PEERS, NB_ERR_ARG, "too many ranks for the peer table");
     NB_CUDA(cudaSetDevice(h->cfg.device));
     NB_CHECK(p2p_prepare(h));
-    cudaIpcMemHandle_t m[3];
+    cudaIpcMemHandle_t m[4];
     NB_CUDA(cudaIpcGetMemHandle(&m[0], h->posw_buf[0]));
     NB_CUDA(cudaIpcGetMemHandle(&m[1], h->posw_buf[1]));
     NB_CUDA(cudaIpcGetMemHandle(&m[2], h->p2p_flags));
+    NB_CUDA(cudaIpcGetMemHandle(&m[3], h->acc_base));
     static_assert(sizeof(m) == NB_P2P_HANDLE_BYTES, "IPC handle size");
     std::memcpy(handles, m, sizeof(m));
     return NB_OK;
@@ -206,13 +260,15 @@ int nb_p2p_attach(nb_handle h, const uint8_t* all_handles)
             h->peer_posw[0][r] = h->posw_buf[0];
             h->peer_posw[1][r] = h->posw_buf[1];
             h->peer_flags[r] = h->p2p_flags;
+            h->peer_acc[r] = h->acc_base;
             continue;
         }
-        cudaIpcMemHandle_t m[3];
+        cudaIpcMemHandle_t m[4];
         std::memcpy(m, all_handles + (size_t)r * NB_P2P_HANDLE_BYTES, sizeof(m));
         NB_CUDA(cudaIpcOpenMemHandle(&h->peer_posw[0][r], m[0], cudaIpcMemLazyEnablePeerAccess));
         NB_CUDA(cudaIpcOpenMemHandle(&h->peer_posw[1][r], m[1], cudaIpcMemLazyEnablePeerAccess));
         NB_CUDA(cudaIpcOpenMemHandle(&h->peer_flags[r], m[2], cudaIpcMemLazyEnablePeerAccess));
+        NB_CUDA(cudaIpcOpenMemHandle(&h->peer_acc[r], m[3], cudaIpcMemLazyEnablePeerAccess));
     }
     h->p2p_ipc = true;
     h->p2p_attached = true;
@@ -243,6 +299,7 @@ int nb_p2p_attach_local(nb_handle h, const nb_handle* peers)
         h->peer_posw[0][r] = p->posw_buf[0];
         h->peer_posw[1][r] = p->posw_buf[1];
         h->peer_flags[r] = p->p2p_flags;
+        h->peer_acc[r] = p->acc_base;
     }
     NB_CUDA(cudaSetDevice(h->cfg.device));
     h->p2p_ipc = false;

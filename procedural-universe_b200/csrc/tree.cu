@@ -24,6 +24,7 @@
 // every rank that holds the same positions builds bit-identical trees.
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "nb_internal.h"
@@ -68,29 +69,50 @@ __device__ __forceinline__ unsigned int axis_cell(double p, double B, double cel
     return (unsigned int)k;
 }
 
+constexpr int MORTON_ITEMS = 4;   // bodies per thread: all loads are issued before the first use
+
 __global__ void __launch_bounds__(256)
 k_morton(const float4* __restrict__ posw, int n, double B, double cell, double inv_cell, unsigned long long* __restrict__ keys,
          unsigned int* __restrict__ vals, unsigned int* __restrict__ counters)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool inside = false;
-    if (i < n)
+    const int base = blockIdx.x * (256 * MORTON_ITEMS) + threadIdx.x;
+    float4 p[MORTON_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MORTON_ITEMS; ++k)
     {
-        const float4 p = posw[i];
-        const float b = (float)B;
-        inside = p.x >= -b && p.y >= -b && p.z >= -b && p.x < b && p.y < b && p.z < b;
-        unsigned long long key = kOutside;
-        if (inside)
-        {
-            const unsigned int qx = axis_cell((double)p.x, B, cell, inv_cell), qy = axis_cell((double)p.y, B, cell, inv_cell),
-                               qz = axis_cell((double)p.z, B, cell, inv_cell);
-            key = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
-        }
-        keys[i] = key;
-        vals[i] = (unsigned int)i;
+        const int i = base + k * 256;
+        p[k] = i < n ? posw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const unsigned int mask = __ballot_sync(0xffffffffu, inside);
-    if ((threadIdx.x & 31) == 0 && mask) atomicAdd(&counters[C_INBOUNDS], __popc(mask));
+    const float b = (float)B;
+    int inside_count = 0;
+#pragma unroll
+    for (int k = 0; k < MORTON_ITEMS; ++k)
+    {
+        const int i = base + k * 256;
+        if (i < n)
+        {
+            const bool inside = p[k].x >= -b && p[k].y >= -b && p[k].z >= -b && p[k].x < b && p[k].y < b && p[k].z < b;
+            unsigned long long key = kOutside;
+            if (inside)
+            {
+                const unsigned int qx = axis_cell((double)p[k].x, B, cell, inv_cell), qy = axis_cell((double)p[k].y, B, cell, inv_cell),
+                                   qz = axis_cell((double)p[k].z, B, cell, inv_cell);
+                key = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+                ++inside_count;
+            }
+            keys[i] = key;
+            vals[i] = (unsigned int)i;
+        }
+    }
+    // one atomic per block, not per warp: 16 M bodies would otherwise queue 512 K updates on one address
+    __shared__ int block_count;
+    if (threadIdx.x == 0) block_count = 0;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) inside_count += __shfl_down_sync(0xffffffffu, inside_count, o);
+    if ((threadIdx.x & 31) == 0 && inside_count) atomicAdd(&block_count, inside_count);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_count) atomicAdd(&counters[C_INBOUNDS], (unsigned int)block_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,10 +306,21 @@ __device__ __forceinline__ int delta_fn(const unsigned long long* __restrict__ k
     return 64 + __clz(i ^ j);
 }
 
+__device__ __forceinline__ int level_of(int prefix_bits)
+{
+    return prefix_bits >= 64 ? kLevels : min(kLevels, (prefix_bits - 1) / 3);
+}
+
+// meta[id] of an internal node = octree level of its cell | 0x100 if it OWNS octree cells (its level is
+// deeper than its parent's).  Written by the parent's thread, which knows both children's ranges and
+// therefore their prefixes; the same thread counts owning nodes per first slot (pre-order ranks).
+constexpr unsigned short kOwns = 0x100;
+
 __global__ void __launch_bounds__(256)
 k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ counters, int leaf_base,
          int2* __restrict__ child, int* __restrict__ prefix, int* __restrict__ parent,
-         unsigned int* __restrict__ flags, int* __restrict__ first_slot)
+         unsigned int* __restrict__ flags, int* __restrict__ first_slot, unsigned short* __restrict__ meta,
+         unsigned int* __restrict__ cnt)
 {
     const int m = (int)counters[C_INBOUNDS];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -317,7 +350,25 @@ k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __rest
     parent[cl] = i;
     parent[cr] = i;
     flags[i] = 0;
-    if (i == 0) parent[0] = kEnd;
+    const int level = level_of(dnode);
+    if (i == 0)
+    {
+        parent[0] = kEnd;
+        meta[0] = (unsigned short)level | kOwns;
+        atomicAdd(&cnt[0], 1u);
+    }
+    if (cl < leaf_base)
+    {
+        const int lc = level_of(delta_fn(keys, m, lo, gamma));
+        meta[cl] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0);
+        if (lc > level) atomicAdd(&cnt[lo], 1u);
+    }
+    if (cr < leaf_base)
+    {
+        const int lc = level_of(delta_fn(keys, m, gamma + 1, hi));
+        meta[cr] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0);
+        if (lc > level) atomicAdd(&cnt[gamma + 1], 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -325,26 +376,9 @@ k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __rest
 // which accumulates the centre of mass in fp32 and overflows for large total mass -- fp64 here).
 // One thread per leaf climbs; the second arrival at a node combines (left + right).
 // ------------------------------------------------------------------------------------------------
-// Node sums are 32-byte records {w, w x, w y, w z} (one sector per node).
-__device__ __forceinline__ void load_node(int id, int leaf_base, const float4* __restrict__ posw,
-                                          const unsigned int* __restrict__ order, const double* nsum,
-                                          double& w, double& sx, double& sy, double& sz)
-{
-    if (id >= leaf_base)
-    {
-        const float4 p = posw[order[id - leaf_base]];
-        w = (double)p.w;
-        sx = w * (double)p.x; sy = w * (double)p.y; sz = w * (double)p.z;
-    }
-    else
-    {
-        // written by another SM earlier in this kernel: read through L2, never a stale L1 line
-        const double2* rec = reinterpret_cast<const double2*>(nsum + 4 * (size_t)id);
-        const double2 a = __ldcg(rec), b = __ldcg(rec + 1);
-        w = a.x; sx = a.y; sy = b.x; sz = b.y;
-    }
-}
-
+// Node sums are 32-byte records {w, w x, w y, w z} (one sector per node).  A climbing thread carries
+// the sums of the subtree it has just completed in registers, so at every level it reads only the
+// SIBLING's record; the child / parent links are fetched alongside the arrival atomic.
 __global__ void __launch_bounds__(256)
 k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ order,
             const unsigned int* __restrict__ counters, int leaf_base, const int2* __restrict__ child,
@@ -353,22 +387,50 @@ k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ or
     const int m = (int)counters[C_INBOUNDS];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m || m < 2) return;
-    int node = parent[leaf_base + j];
-    while (node != kEnd)
+    int id = leaf_base + j;
+    int node = parent[id];
+    double w, sx, sy, sz;
     {
-        // One acq_rel atomic instead of fence + atomic + fence: the release half publishes the record this
-        // thread stored one level below, the acquire half orders the sibling's record before the loads.
-        unsigned int arrived;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(arrived) : "l"(flags + node), "r"(1u) : "memory");
-        if (arrived == 0u) return;                       // first arrival: the sibling subtree is not done
+        const float4 p = posw[order[j]];
+        w = (double)p.w;
+        sx = w * (double)p.x; sy = w * (double)p.y; sz = w * (double)p.z;
+    }
+    for (;;)
+    {
         const int2 c = child[node];
-        double wl, lx, ly, lz, wr, rx, ry, rz;
-        load_node(c.x, leaf_base, posw, order, nsum, wl, lx, ly, lz);
-        load_node(c.y, leaf_base, posw, order, nsum, wr, rx, ry, rz);
+        const int up = parent[node];
+        // Arrival counter.  Release (level >= 2) publishes the record this thread stored one level below;
+        // a leaf has stored nothing, so level 1 is relaxed.  No acquire half (it costs an L1 invalidate per
+        // level): the sibling's record is read with ld.global.cg -- L2, where the release made it visible
+        // before the counter moved -- and that load cannot issue before the branch on `arrived` resolves.
+        unsigned int arrived;
+        if (id >= leaf_base)
+            asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], %2;" : "=r"(arrived) : "l"(flags + node), "r"(1u) : "memory");
+        else
+            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(arrived) : "l"(flags + node), "r"(1u) : "memory");
+        if (arrived == 0u) return;                       // first arrival: the sibling subtree is not done
+        const int sib = (c.x == id) ? c.y : c.x;
+        double ow, ox, oy, oz;
+        if (sib >= leaf_base)
+        {
+            const float4 p = posw[order[sib - leaf_base]];
+            ow = (double)p.w;
+            ox = ow * (double)p.x; oy = ow * (double)p.y; oz = ow * (double)p.z;
+        }
+        else
+        {
+            // written by another SM earlier in this kernel: read through L2, never a stale L1 line
+            const double2* rec = reinterpret_cast<const double2*>(nsum + 4 * (size_t)sib);
+            const double2 a = __ldcg(rec), b = __ldcg(rec + 1);
+            ow = a.x; ox = a.y; oy = b.x; oz = b.y;
+        }
+        w += ow; sx += ox; sy += oy; sz += oz;           // fp64 addition commutes: left + right either way
         double2* rec = reinterpret_cast<double2*>(nsum + 4 * (size_t)node);
-        rec[0] = make_double2(wl + wr, lx + rx);
-        rec[1] = make_double2(ly + ry, lz + rz);
-        node = parent[node];
+        rec[0] = make_double2(w, sx);
+        rec[1] = make_double2(sy, sz);
+        if (up == kEnd) return;
+        id = node;
+        node = up;
     }
 }
 
@@ -377,17 +439,7 @@ k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ or
 // next-if-skipped, body}.  Threshold: leaves -1 (always evaluated), owning nodes (width/theta)^2,
 // nodes that own no octree cell are skipped by the pointers.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int level_of(int prefix_bits)
-{
-    return prefix_bits >= 64 ? kLevels : min(kLevels, (prefix_bits - 1) / 3);
-}
-
-__device__ __forceinline__ bool owns_cell(int id, const int* __restrict__ prefix, const int* __restrict__ parent)
-{
-    const int p = parent[id];
-    if (p == kEnd) return true;
-    return level_of(prefix[id]) > level_of(prefix[p]);
-}
+__device__ __forceinline__ bool owns_cell(int id, const unsigned short* __restrict__ meta) { return (meta[id] & kOwns) != 0; }
 
 // K6b: depth-first (pre-order) layout of the nodes the traversal can visit -- leaves and the
 // radix-tree nodes that own an octree cell.  Opening a node then means "next record" and skipping
@@ -398,15 +450,6 @@ __device__ __forceinline__ bool owns_cell(int id, const int* __restrict__ prefix
 // With cnt[f] = #owning nodes whose range starts at slot f and P = exclusive scan of cnt:
 //   rank(node v) = first(v) + P[first(v)] + #owning proper ancestors with the same first
 //   rank(leaf j) = j + P[j + 1]
-__global__ void __launch_bounds__(256)
-k_count_owned(const unsigned int* __restrict__ counters, const int* __restrict__ prefix, const int* __restrict__ parent,
-              const int* __restrict__ first_slot, unsigned int* __restrict__ cnt)
-{
-    const int m = (int)counters[C_INBOUNDS];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m - 1 && owns_cell(i, prefix, parent)) atomicAdd(&cnt[first_slot[i]], 1u);
-}
-
 __global__ void __launch_bounds__(256)
 k_scan_apply(const unsigned int* __restrict__ in, int n, const unsigned int* __restrict__ block_prefix,
              unsigned int* __restrict__ out)
@@ -441,21 +484,21 @@ k_scan_apply(const unsigned int* __restrict__ in, int n, const unsigned int* __r
 
 __global__ void __launch_bounds__(256)
 k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int2* __restrict__ child,
-       const int* __restrict__ prefix, const int* __restrict__ parent, const int* __restrict__ first_slot,
+       const unsigned short* __restrict__ meta, const int* __restrict__ parent, const int* __restrict__ first_slot,
        const unsigned int* __restrict__ pref, int* __restrict__ rank)
 {
     const int m = (int)counters[C_INBOUNDS];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) counters[C_TOTAL] = (unsigned int)m + pref[n];
     if (t < m) rank[leaf_base + t] = t + (int)pref[t + 1];
-    if (t < m - 1 && owns_cell(t, prefix, parent))
+    if (t < m - 1 && owns_cell(t, meta))
     {
         int above = 0, v = t;
         for (;;)
         {
             const int p = parent[v];
             if (p == kEnd || child[p].x != v) break;
-            if (owns_cell(p, prefix, parent)) ++above;
+            if (owns_cell(p, meta)) ++above;
             v = p;
         }
         const int f = first_slot[t];
@@ -465,7 +508,7 @@ k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int2* __
 
 // The record after the subtree of `id` in pre-order (kEnd if none).
 __device__ __forceinline__ int after_subtree(int id, int leaf_base, const int2* __restrict__ child,
-                                             const int* __restrict__ prefix, const int* __restrict__ parent)
+                                             const unsigned short* __restrict__ meta, const int* __restrict__ parent)
 {
     for (;;)
     {
@@ -475,7 +518,7 @@ __device__ __forceinline__ int after_subtree(int id, int leaf_base, const int2* 
         if (c.x == id)
         {
             int r = c.y;
-            while (r < leaf_base && !owns_cell(r, prefix, parent)) r = child[r].x;
+            while (r < leaf_base && !owns_cell(r, meta)) r = child[r].x;
             return r;
         }
         id = p;
@@ -488,7 +531,7 @@ __device__ __forceinline__ int after_subtree(int id, int leaf_base, const int2* 
 __global__ void __launch_bounds__(256)
 k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ counters,
            int leaf_base, const int2* __restrict__ child,
-           const int* __restrict__ prefix, const int* __restrict__ parent, const double* __restrict__ nsum,
+           const unsigned short* __restrict__ meta, const int* __restrict__ parent, const double* __restrict__ nsum,
            float root_width, float inv_theta,
            const int* __restrict__ rank, float4* __restrict__ nodes)
 {
@@ -503,16 +546,16 @@ k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ ord
         nodes[2 * (size_t)r] = make_float4(p.x, p.y, p.z, p.w * kPreScale);
         nodes[2 * (size_t)r + 1] = make_float4(-1.0f, __int_as_float(r + 1), __int_as_float((int)body), 0.f);
     }
-    if (t < m - 1 && owns_cell(t, prefix, parent))
+    if (t < m - 1 && owns_cell(t, meta))
     {
         const int r = rank[t];
-        const int nxt = after_subtree(t, leaf_base, child, prefix, parent);
+        const int nxt = after_subtree(t, leaf_base, child, meta, parent);
         const int skip = nxt == kEnd ? total : rank[nxt];
         const double2* rec = reinterpret_cast<const double2*>(nsum + 4 * (size_t)t);
         const double2 s0 = rec[0], s1 = rec[1];
         const double w = s0.x;
         const double inv = w != 0.0 ? 1.0 / w : 0.0;
-        const float width = ldexpf(root_width, -level_of(prefix[t]));
+        const float width = ldexpf(root_width, -(int)(meta[t] & 0xff));
         const float lim = width * inv_theta;
         nodes[2 * (size_t)r] = make_float4((float)(s0.y * inv), (float)(s1.x * inv), (float)(s1.y * inv), (float)w * kPreScale);
         nodes[2 * (size_t)r + 1] = make_float4(lim * lim, __int_as_float(skip), __int_as_float(-1), 0.f);
@@ -528,22 +571,27 @@ k_finalize(const float4* __restrict__ posw, const unsigned int* __restrict__ ord
 // Interaction: same law as all-pairs, a += G M (c - p) / (|d| (d^2 + S)); the self term and
 // coincident bodies vanish through the epsilon (see allpairs.cuh).
 // ------------------------------------------------------------------------------------------------
-template <bool STATS, int GROUP>
+// BALANCED (world > 1 with peer memory attached): the Morton-ordered list of ALL bodies is dealt out
+// block by block -- this rank takes blocks rank, rank + world, ... -- so every rank walks the same mix
+// of dense and sparse regions, and each lane stores its acceleration straight into the acc array of the
+// body's owner (local or over NVLink); the owners' kick-drift waits for the accelerations (p2p.cu).
+template <bool STATS, int GROUP, bool BALANCED>
 __global__ void __launch_bounds__(256)
 k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ tlist,
        int ntargets, const unsigned int* __restrict__ counters, const float4* __restrict__ nodes,
-       int first, int count, float sc, double* __restrict__ acc, unsigned long long* __restrict__ stats)
+       int first, int count, float sc, double* __restrict__ acc, unsigned long long* __restrict__ stats, AccTable owners)
 {
     // GROUP consecutive lanes share one traversal pointer (32 = the whole warp, the default).  Smaller
     // groups walk a smaller union of subtrees, but the warp runs until its slowest group is done and the
     // vote costs more: measured at 16 M bodies 37.6 ms (32) / 42.0 ms (16) / 40.9 ms (8).
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = BALANCED ? (blockIdx.x * owners.world + owners.rank) * 256 + threadIdx.x
+                           : blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = t < ntargets;
     unsigned int body = 0;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid)
     {
-        body = order[tlist ? tlist[t] : (unsigned int)t];
+        body = order[(!BALANCED && tlist) ? tlist[t] : (unsigned int)t];
         p = posw[body];
     }
     const int total = (int)counters[C_TOTAL];
@@ -591,7 +639,20 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
         else open = (__ballot_sync(0xffffffffu, active && !accept) & gmask) != 0u;
         if (live) cur = open ? cur + 1 : skip;
     }
-    if (valid)
+    if (valid && BALANCED)
+    {
+        // owner of `body` under the block partition first[r] = r * n / world
+        int o = (int)(((unsigned long long)body * (unsigned long long)owners.world) / (unsigned long long)owners.first[owners.world]);
+        while (o > 0 && (int)body < owners.first[o]) --o;
+        while (o + 1 < owners.world && (int)body >= owners.first[o + 1]) ++o;
+        const size_t cnt = (size_t)(owners.first[o + 1] - owners.first[o]);
+        const size_t li = (size_t)((int)body - owners.first[o]);
+        double* dst = owners.acc[o] + (size_t)owners.parity * 3 * cnt;
+        dst[li] = (double)ax;
+        dst[cnt + li] = (double)ay;
+        dst[2 * cnt + li] = (double)az;
+    }
+    else if (valid)
     {
         const int li = (int)body - first;
         if (li >= 0 && li < count)
@@ -692,7 +753,7 @@ void tree_release(nb_sim* h)
     for (int k = 0; k < 2; ++k) { cudaFree(t.keys[k]); cudaFree(t.vals[k]); t.keys[k] = nullptr; t.vals[k] = nullptr; }
     cudaFree(t.hist); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
     cudaFree(t.range); cudaFree(t.flags); cudaFree(t.nsum); cudaFree(t.walk_a);
-    cudaFree(t.walk_b); cudaFree(t.stats); cudaFree(t.cnt); cudaFree(t.pref); cudaFree(t.rank); cudaFree(t.tlist);
+    cudaFree(t.walk_b); cudaFree(t.stats); cudaFree(t.cnt); cudaFree(t.pref); cudaFree(t.rank); cudaFree(t.tlist); cudaFree(t.meta);
     t = TreeBuffers();
 }
 
@@ -718,6 +779,7 @@ int tree_reserve(nb_sim* h)
     NB_CUDA(cudaMalloc(&t.cnt, (n + 1) * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.pref, (n + 1) * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.rank, 2 * n * sizeof(int)));
+    NB_CUDA(cudaMalloc(&t.meta, n * sizeof(unsigned short)));
     NB_CUDA(cudaMalloc(&t.tlist, n * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.flags, n * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.nsum, 4 * n * sizeof(double)));
@@ -738,7 +800,7 @@ int tree_build(nb_sim* h)
 
     NB_CUDA(cudaMemsetAsync(t.counters, 0, C_WORDS * sizeof(unsigned int), st));
     const double cell = std::ldexp((double)h->cfg.bounds, 1 - kLevels);      // 2B / 2^21, exact
-    k_morton<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, cell, 1.0 / cell, t.keys[0], t.vals[0], t.counters);
+    k_morton<<<blocks_for(n, 256 * MORTON_ITEMS), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, cell, 1.0 / cell, t.keys[0], t.vals[0], t.counters);
     ++h->last_launches;
 
     unsigned int* totals = t.hist + (size_t)256 * tiles;
@@ -764,23 +826,23 @@ int tree_build(nb_sim* h)
     NB_CUDA(cudaGetLastError());
 
     const int leaf_base = n;
-    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range);
+    const int words = n + 1;
+    NB_CUDA(cudaMemsetAsync(t.cnt, 0, (size_t)words * sizeof(unsigned int), st));
+    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range,
+                                                t.meta, t.cnt);
     k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.parent, t.flags, t.nsum);
-    // pre-order ranks: count owning nodes per first slot, exclusive scan, rank, then the records
+    // pre-order ranks: owning nodes per first slot were counted by k_karras; exclusive scan, rank, then the records
     {
-        const int words = n + 1;
         const int sblocks = (words + 4095) / 4096;
         unsigned int* sums = t.hist;                 // radix-sort scratch is free again
         unsigned int* total = t.hist + sblocks;
-        NB_CUDA(cudaMemsetAsync(t.cnt, 0, (size_t)words * sizeof(unsigned int), st));
-        k_count_owned<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, t.prefix, t.parent, t.range, t.cnt);
         k_block_sums<<<sblocks, 256, 0, st>>>(t.cnt, words, sums);
         k_rs_scan_rows<<<1, 256, 0, st>>>(sums, sblocks, total);
         k_scan_apply<<<sblocks, 256, 0, st>>>(t.cnt, words, sums, t.pref);
-        k_rank<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, n, leaf_base, t.child, t.prefix, t.parent, t.range, t.pref, t.rank);
-        h->last_launches += 5;
+        k_rank<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, n, leaf_base, t.child, t.meta, t.parent, t.range, t.pref, t.rank);
+        h->last_launches += 4;
     }
-    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.prefix,
+    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.meta,
                                                   t.parent, t.nsum, 2.0f * h->cfg.bounds, 1.0f / h->cfg.theta, t.rank, t.walk_a);
     h->last_launches += 3;
     NB_CUDA(cudaGetLastError());
@@ -790,12 +852,27 @@ int tree_build(nb_sim* h)
 
 static bool g_walk_stats = false;
 
-int tree_walk(nb_sim* h)
+int tree_walk(nb_sim* h, bool balanced)
 {
     TreeBuffers& t = h->tree;
     const int n = (int)h->n;
     cudaStream_t st = h->stream;
     const unsigned int* order = t.vals[t.cur];
+    const float sc = (float)(h->cfg.softening * (double)kPreScale);
+    AccTable owners;
+    std::memset(&owners, 0, sizeof(owners));
+    if (balanced && !g_walk_stats)
+    {
+        NB_CHECK(p2p_acc_table(h, &owners));
+        const int all_blocks = blocks_for(n, 256);
+        const int blocks = (all_blocks - h->cfg.rank + h->cfg.world - 1) / h->cfg.world;
+        if (blocks > 0)
+            k_walk<false, 32, true><<<blocks, 256, 0, st>>>(h->posw, order, nullptr, n, t.counters, t.walk_a, (int)h->first,
+                                                           (int)h->count, sc, h->acc, t.stats, owners);
+        ++h->last_launches;
+        NB_CUDA(cudaGetLastError());
+        return NB_OK;
+    }
     const unsigned int* tlist = nullptr;
     int ntargets = n;
     if (h->cfg.world > 1)
@@ -813,11 +890,10 @@ int tree_walk(nb_sim* h)
         tlist = t.tlist;
         ntargets = (int)h->count;
     }
-    const float sc = (float)(h->cfg.softening * (double)kPreScale);
     const int blocks = blocks_for(ntargets, 256);
 #define NB_WALK(STATS, GROUP)                                                                                            \
-    k_walk<STATS, GROUP><<<blocks, 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, \
-                                                 (int)h->count, sc, h->acc, t.stats)
+    k_walk<STATS, GROUP, false><<<blocks, 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, \
+                                                        (int)h->count, sc, h->acc, t.stats, owners)
     // kernel_variant 1 / 2: 16- / 8-lane groups (measured slower, kept for the record: DESIGN.md K7)
     const int group = h->cfg.kernel_variant == 1 ? 16 : (h->cfg.kernel_variant == 2 ? 8 : 32);
     if (g_walk_stats)

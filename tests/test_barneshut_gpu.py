@@ -244,6 +244,41 @@ def test_sharded_ranks_reproduce_single_gpu_bitwise(pkg):
     one.close()
 
 
+def test_balanced_walk_over_peer_memory_reproduces_single_gpu_bitwise(pkg):
+    """csrc/p2p.cu + tree.cu: with peer memory attached nb_step deals the Morton-ordered target list out
+    to the ranks block by block and every rank stores the accelerations it computed straight into their
+    owner's array (here: three shard handles on one GPU attached by handle), then the fused kick-drift
+    pushes positions.  A lane's result does not depend on which rank or warp walks it, so after k steps
+    the shards hold exactly what a single handle holds -- including bodies that left the root cube."""
+    p = pkg.seed_galaxy_host(6000, 21, 1.0)
+    p["Position"][100:110] *= 40.0                     # some bodies outside the cube: targets only
+    dt, steps, world = 0.02 / 60, 7, 3
+    one = bh(pkg, theta=0.5)
+    one.init(p)
+    one.step(dt, steps)
+    want = p.copy()
+    one.read(want)
+    shards = [bh(pkg, theta=0.5, rank=r, world=world) for r in range(world)]
+    for s in shards:
+        s.init(p)
+    for s in shards:
+        s.p2p_attach_local(shards)
+    for _ in range(steps):
+        for s in shards:
+            s.step(dt, 1)                              # one host thread drives all ranks, like one step of every process
+    got = p.copy()
+    for s in shards:
+        s.read(got)                                    # each writes its owned range
+    assert np.array_equal(got["Position"], want["Position"])
+    assert np.array_equal(got["Velocity"], want["Velocity"])
+    assert np.array_equal(got["Forces"], want["Forces"])          # BarnesHut leaves m*a of the last step
+    acc = np.concatenate([s.accelerations() for s in shards])
+    assert np.array_equal(acc, one.accelerations())
+    for s in shards:
+        s.close()
+    one.close()
+
+
 def test_large_n_sampled_parity(pkg):
     """configs[3] shape at N = 262144: sampled targets against the reference walk."""
     n = 1 << 18
