@@ -193,6 +193,11 @@ NB_API int nb_get_morton(nb_handle h, uint64_t* codes, uint32_t* order, size_t* 
  * mass and centre of mass.  Any pointer may be NULL. */
 NB_API int nb_get_tree(nb_handle h, int32_t* left, int32_t* right, int32_t* prefix_bits, double* mass,
                 float* com3, size_t* n_internal);
+/* BarnesHut::RenderDebug -> Octree::RenderDebug (BarnesHut.cpp:98-101, Octree.cpp:147-175): the reference
+ * draws one cube per OCCUPIED LEAF of its octree.  For the current positions: cells4[4*k] = {centre.x,
+ * centre.y, centre.z, size} of the leaf holding in-bounds body body[k], k in Morton order (the order of
+ * the reference's recursion over children 0..7).  Either output may be NULL. */
+NB_API int nb_get_leaf_cells(nb_handle h, float* cells4, uint32_t* body, size_t* n_inbounds);
 /* Counters of the last traversal summed over owned targets: {accepted cells, pair (leaf)
  * evaluations, node visits}. */
 NB_API int nb_get_walk_stats(nb_handle h, uint64_t stats3[3]);

@@ -65,6 +65,8 @@ def lib():
         L.ref_octree_cell.argtypes = [vp, sz, C.c_int, C.c_uint64, dp, C.POINTER(C.c_float),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_float)]
         L.ref_octree_cell.restype = C.c_int
+        L.ref_octree_leaf_cubes.argtypes = [vp, sz, fp, i64p]
+        L.ref_octree_leaf_cubes.restype = C.c_size_t
         L.ref_barneshut_work.argtypes = [vp, sz, C.c_double, i64p, sz, i64p]
         L.ref_report_theta.argtypes = [C.c_float]
         L.ref_get_theta.restype = C.c_double
@@ -176,6 +178,16 @@ def octree_paths(p):
                            path.ctypes.data_as(C.POINTER(C.c_uint64)), _i64(stats))
     return depth, path, dict(nodes=int(stats[0]), internal=int(stats[1]), max_depth=int(stats[2]),
                              root_count=int(stats[3]))
+
+
+def octree_leaf_cubes(p):
+    """What Octree::RenderDebug draws: (cubes[k] = {pos.xyz, size}, body[k]) for every occupied leaf, in the
+    reference's recursion order (children 0..7 = Morton order)."""
+    n = len(p)
+    out = np.zeros((n, 4), dtype=np.float32)
+    body = np.zeros(n, dtype=np.int64)
+    k = lib().ref_octree_leaf_cubes(_vp(p), n, out.ctypes.data_as(C.POINTER(C.c_float)), _i64(body))
+    return out[:k], body[:k]
 
 
 def octree_cell(p, depth, path):

@@ -368,6 +368,32 @@ extern "C"
         }
     }
 
+    // What Octree::RenderDebug draws (Octree.cpp:147-175): one cube per OCCUPIED LEAF, at
+    // pos = (TopLeft + BottomRight) / 2 with size = BottomRight.x - TopLeft.x.  Collected by the same
+    // recursion; out4[k] = {pos.x, pos.y, pos.z, size}, body[k] = index of the leaf's particle.
+    static void CollectLeafCubes(Octree* t, const Particle* base, float* out4, int64_t* body, size_t* count)
+    {
+        if (t->IsLeaf && t->NumParticles > 0)
+        {
+            auto avg = (t->Bounds.TopLeft + t->Bounds.BottomRight) / 2;
+            const size_t k = (*count)++;
+            out4[4 * k + 0] = avg.x; out4[4 * k + 1] = avg.y; out4[4 * k + 2] = avg.z;
+            out4[4 * k + 3] = t->Bounds.BottomRight.x - t->Bounds.TopLeft.x;
+            body[k] = static_cast<int64_t>(t->P - base);
+        }
+        if (!t->IsLeaf)
+            for (auto& child : t->Children) CollectLeafCubes(child.get(), base, out4, body, count);
+    }
+
+    size_t ref_octree_leaf_cubes(const void* aos, size_t n, float* out4, int64_t* body)
+    {
+        std::vector<Particle> v = ToVector(aos, n);
+        std::unique_ptr<Octree> tree = BuildTree(v, 0.5);
+        size_t count = 0;
+        CollectLeafCubes(tree.get(), v.data(), out4, body, &count);
+        return count;
+    }
+
     // Mass / centre of mass / population of the cell reached from the root by `depth` digits of
     // `path` (same packing as above).  Returns 0 on success, 1 if the path leaves the tree.
     int ref_octree_cell(const void* aos, size_t n, int depth, uint64_t path, double* mass, float* com3,

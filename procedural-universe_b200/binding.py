@@ -106,6 +106,7 @@ def load():
     L.nb_get_morton.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_get_tree.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     L.nb_get_walk_stats.argtypes = [vp, vp]
+    L.nb_get_leaf_cells.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_energy.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
     L.nb_energy_sampled.argtypes = [vp, sz, C.POINTER(f64), C.POINTER(f64), C.POINTER(sz)]
     L.nb_closest_particle.argtypes = [vp, C.POINTER(f32), C.POINTER(sz), C.POINTER(f32)]
@@ -315,6 +316,15 @@ class Sim:
         ke, pe = C.c_double(), C.c_double()
         _check(self._L.nb_energy(self._h, C.byref(ke), C.byref(pe)))
         return ke.value, pe.value
+
+    def leaf_cells(self):
+        """(cubes[k] = {centre.xyz, size}, body[k]) of the occupied octree leaves, Morton order."""
+        n = C.c_size_t()
+        _check(self._L.nb_get_leaf_cells(self._h, None, None, C.byref(n)))
+        cells = np.zeros((n.value, 4), dtype=np.float32)
+        body = np.zeros(n.value, dtype=np.uint32)
+        _check(self._L.nb_get_leaf_cells(self._h, cells.ctypes.data, body.ctypes.data, C.byref(n)))
+        return cells, body
 
     def closest_particle(self, pos):
         """Maths::ClosestParticle on the device-resident positions -> (index, distance squared)."""

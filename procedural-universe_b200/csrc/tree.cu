@@ -676,6 +676,39 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
     }
 }
 
+// Debug export: what BarnesHut::RenderDebug -> Octree::RenderDebug draws (Octree.cpp:147-175) -- one
+// cube per occupied leaf.  A body's leaf sits one level below the deepest cell it shares with a
+// neighbour in the sorted order (level 0, the root cube, if it is alone; level 21 for duplicates).
+__device__ __forceinline__ unsigned int compact3(unsigned long long x)
+{
+    x &= 0x1249249249249249ull;
+    x = (x | x >> 2) & 0x10c30c30c30c30c3ull;
+    x = (x | x >> 4) & 0x100f00f00f00f00full;
+    x = (x | x >> 8) & 0x1f0000ff0000ffull;
+    x = (x | x >> 16) & 0x1f00000000ffffull;
+    x = (x | x >> 32) & 0x1fffffull;
+    return (unsigned int)x;
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_cells(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ counters, double B,
+             float4* __restrict__ cells)
+{
+    const int m = (int)counters[C_INBOUNDS];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int shared = max(delta_fn(keys, m, j, j - 1), delta_fn(keys, m, j, j + 1));
+    const int depth = shared < 0 ? 0 : min(kLevels, level_of(shared) + 1);
+    const unsigned long long k = keys[j];
+    const int drop = kLevels - depth;                               // axis bits below the leaf's level
+    const double width = ldexp(2.0 * B, -depth);
+    const double x = -B + (double)(compact3(k) >> drop) * width;
+    const double y = -B + (double)(compact3(k >> 1) >> drop) * width;
+    const double z = -B + (double)(compact3(k >> 2) >> drop) * width;
+    const double half = 0.5 * width;
+    cells[j] = make_float4((float)(x + half), (float)(y + half), (float)(z + half), (float)width);
+}
+
 // Owned targets in Morton order (world > 1): slots whose body index lies in [first, first+count).
 __global__ void __launch_bounds__(256)
 k_select_flags(const unsigned int* __restrict__ order, int n, int first, int count, unsigned int* __restrict__ flag)
@@ -970,6 +1003,33 @@ int nb_get_tree(nb_handle h, int32_t* left, int32_t* right, int32_t* prefix_bits
                 for (int c = 0; c < 3; ++c) com3[3 * i + c] = (float)(w != 0.0 ? s4[4 * i + 1 + c] / w : 0.0);
         }
     }
+    return NB_OK;
+}
+
+int nb_get_leaf_cells(nb_handle h, float* cells4, uint32_t* body, size_t* n_inbounds)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(h->cfg.mode == NB_MODE_BARNESHUT, NB_ERR_STATE, "handle is not in Barnes-Hut mode");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->tree.built) NB_CHECK(tree_build(h));
+    TreeBuffers& t = h->tree;
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned int m = 0;
+    NB_CUDA(cudaMemcpy(&m, t.counters + C_INBOUNDS, sizeof(m), cudaMemcpyDeviceToHost));
+    if (n_inbounds) *n_inbounds = m;
+    if (m == 0) return NB_OK;
+    if (cells4)
+    {
+        float4* d = reinterpret_cast<float4*>(t.nsum);           // node sums are rebuilt by the next tree_build
+        k_leaf_cells<<<blocks_for(m, 256), 256, 0, h->stream>>>(t.keys[t.cur], t.counters, (double)h->cfg.bounds, d);
+        NB_CUDA(cudaGetLastError());
+        NB_CUDA(cudaMemcpyAsync(cells4, d, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+        NB_CUDA(cudaStreamSynchronize(h->stream));
+        t.built = false;                                         // the scratch overwrote the node sums
+        ++h->total_launches;
+    }
+    if (body) NB_CUDA(cudaMemcpy(body, t.vals[t.cur], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return NB_OK;
 }
 

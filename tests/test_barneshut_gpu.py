@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import as_particles, load_golden, rel_err
-from oracle import checker, port
+from oracle import checker, port, ref
 
 pytestmark = pytest.mark.gpu
 
@@ -387,3 +387,29 @@ def test_energy_drift_at_65536_bodies_tracks_the_reference(pkg):
     assert drift[-1] <= 2.0 * g["drift"][-1] and drift.max() <= 2.0 * g["drift"].max()
     assert np.all(np.abs(drift[1:] - g["drift"][1:]) <= 0.25 * g["drift"][1:] + 1e-5)
     sim.close()
+
+
+def test_leaf_cells_are_the_cubes_the_reference_draws(pkg):
+    """nb_get_leaf_cells against BarnesHut::RenderDebug (Octree.cpp:147-175): one cube per occupied leaf,
+    same bodies in the same (recursion = Morton) order, same centre and size.  The reference derives its
+    bounds by repeated fp32 halving, exact for the levels these scenes reach."""
+    for p in (pkg.seed_galaxy_host(1024, 42, 1.0), scattered(pkg, 3000, 5, duplicates=False), pkg.seed_galaxy_host(1, 3, 1.0)):
+        sim = bh(pkg)
+        sim.init(p)
+        cells, body = sim.leaf_cells()
+        if ref.available():
+            want, want_body = ref.octree_leaf_cubes(p)
+            assert np.array_equal(body, want_body)
+            assert np.array_equal(cells[:, 3], want[:, 3])
+            assert np.abs(cells[:, :3] - want[:, :3]).max() <= 1e-3
+            exact = want[:, 3] >= 8000.0 / 2 ** 16
+            assert np.array_equal(cells[exact], want[exact])
+        depth, path = port.octree_paths(p)[:2]
+        inb = depth[body] >= 0
+        assert inb.all() and np.array_equal(cells[:, 3], (8000.0 / 2.0 ** depth[body]).astype(np.float32))
+        inside = np.all(np.abs(p["Position"][body] - cells[:, :3]) <= cells[:, 3:4] / 2, axis=1)
+        assert inside.all()                                   # every body lies in its cube
+        # the export used the node-sum scratch: the next force evaluation rebuilds the tree
+        acc = sim.accelerations()
+        assert np.all(np.isfinite(acc))
+        sim.close()
