@@ -5,6 +5,7 @@
 // the B200 adapter through the reference's own INBodySim interface and factory names, exactly as
 // SimulationState does (Init on a std::vector<Particle>, then Update(dt) per frame,
 // SimulationState.cpp:52-53, 218-227), so the parity test reads like the reference's usage.
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -94,5 +95,33 @@ extern "C"
         if (impl == 1) static_cast<B200Sim*>(sim.get())->Shutdown();
         sim.release();   // never destroy a reference sim on glibc (~CThreadPool deadlocks)
         return 0;
+    }
+
+    // Sim->RenderDebug(view, proj) through the interface (SimulationState.cpp:81) after `steps` Updates,
+    // on a sim that was given a (never dereferenced) D3D context so that it owns a debug Cube.  Returns
+    // the number of cubes drawn; the first `cap` {x, y, z, size} records are copied to out4.
+    long adapter_debug_cubes(void* aos, size_t n, int impl, float dt, int steps, float theta, float* out4, size_t cap)
+    {
+        std::vector<Particle> particles(n);
+        std::memcpy(static_cast<void*>(particles.data()), aos, n * sizeof(Particle));
+        Octree::Theta = theta;
+        ID3D11DeviceContext* context = reinterpret_cast<ID3D11DeviceContext*>(static_cast<uintptr_t>(16));
+        std::unique_ptr<INBodySim> sim;
+        {
+            Quiet q;
+            sim = impl == 0 ? CreateNBodySim(context, ENBodySim::BarnesHut) : CreateB200NBodySim(context, ENBodySim::BarnesHut);
+        }
+        if (!sim) return -1;
+        if (impl == 0) static_cast<BarnesHut*>(sim.get())->Pool.SetNumWorkers(n % 4 == 0 ? 4 : 1);
+        sim->Init(particles);
+        for (int s = 0; s < steps; ++s) sim->Update(dt);
+        Cube::Drawn().clear();
+        sim->RenderDebug(DirectX::SimpleMath::Matrix(), DirectX::SimpleMath::Matrix());
+        const std::vector<float>& d = Cube::Drawn();
+        const size_t cubes = d.size() / 4;
+        if (out4 && cap) std::memcpy(out4, d.data(), sizeof(float) * 4 * (cubes < cap ? cubes : cap));
+        if (impl == 1) static_cast<B200Sim*>(sim.get())->Shutdown();
+        sim.release();
+        return static_cast<long>(cubes);
     }
 }

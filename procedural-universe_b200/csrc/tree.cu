@@ -1021,12 +1021,11 @@ int nb_get_leaf_cells(nb_handle h, float* cells4, uint32_t* body, size_t* n_inbo
     if (m == 0) return NB_OK;
     if (cells4)
     {
-        float4* d = reinterpret_cast<float4*>(t.nsum);           // node sums are rebuilt by the next tree_build
+        float4* d = t.walk_a;      // scratch: the traversal records are rewritten by every tree_build before a walk reads them
         k_leaf_cells<<<blocks_for(m, 256), 256, 0, h->stream>>>(t.keys[t.cur], t.counters, (double)h->cfg.bounds, d);
         NB_CUDA(cudaGetLastError());
         NB_CUDA(cudaMemcpyAsync(cells4, d, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
         NB_CUDA(cudaStreamSynchronize(h->stream));
-        t.built = false;                                         // the scratch overwrote the node sums
         ++h->total_launches;
     }
     if (body) NB_CUDA(cudaMemcpy(body, t.vals[t.cur], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));

@@ -10,7 +10,7 @@ static_assert(sizeof(Particle) == NB_PARTICLE_STRIDE, "Particle layout differs f
 static_assert(offsetof(Particle, Velocity) == NB_OFF_VELOCITY && offsetof(Particle, Forces) == NB_OFF_FORCES &&
               offsetof(Particle, Mass) == NB_OFF_MASS, "Particle layout differs from the one the engine was built for");
 
-B200Sim::B200Sim(ID3D11DeviceContext*, EMode mode, int device) : Mode(mode)
+B200Sim::B200Sim(ID3D11DeviceContext* context, EMode mode, int device) : Mode(mode)
 {
     LOGM(mode == EMode::AllPairs ? "Brute Force B200" : "Barnes-Hut B200")
 
@@ -25,6 +25,9 @@ B200Sim::B200Sim(ID3D11DeviceContext*, EMode mode, int device) : Mode(mode)
         Handle = nullptr;                                    // Update() becomes a logged no-op, like
         return;                                              // BruteForceGPU without its shader (:25-33)
     }
+
+    if (context && mode == EMode::BarnesHut)
+        DebugCube = std::make_unique<Cube>(context);         // BarnesHut.cpp:23-27
 
     if (mode == EMode::BarnesHut)
     {
@@ -91,6 +94,22 @@ void B200Sim::Update(float dt)
     if (Pinned != Particles->data() || PinnedBytes != Particles->size() * sizeof(Particle)) Pin();
     if (nb_update_aos(Handle, Particles->data(), Particles->size(), sizeof(Particle), dt) != NB_OK)
         LOGE(std::string("B200Sim::Update: ") + nb_last_error())
+}
+
+void B200Sim::RenderDebug(DirectX::SimpleMath::Matrix view, DirectX::SimpleMath::Matrix proj)
+{
+    if (!Handle || !DebugCube || Mode != EMode::BarnesHut) return;
+    size_t n = 0;
+    if (nb_get_leaf_cells(Handle, nullptr, nullptr, &n) != NB_OK || n == 0) return;
+    DebugCells.resize(4 * n);
+    if (nb_get_leaf_cells(Handle, DebugCells.data(), nullptr, &n) != NB_OK)
+    {
+        LOGE(std::string("B200Sim::RenderDebug: ") + nb_last_error())
+        return;
+    }
+    for (size_t k = 0; k < n; ++k)      // Octree::RenderDebug: cube->Render(pos, size, view * proj), Octree.cpp:166
+        DebugCube->Render(DirectX::SimpleMath::Vector3(DebugCells[4 * k], DebugCells[4 * k + 1], DebugCells[4 * k + 2]),
+                          DebugCells[4 * k + 3], view * proj);
 }
 
 std::unique_ptr<INBodySim> CreateB200NBodySim(ID3D11DeviceContext* context, ENBodySim type)

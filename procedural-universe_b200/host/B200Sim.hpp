@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "Sim/INBodySim.hpp"
+#include "Render/Model/Cube.hpp"
 
 #include "nbody_b200.h"
 
@@ -30,6 +31,9 @@ class B200Sim : public INBodySim
 
         void Init(std::vector<Particle>& particles) override;
         void Update(float dt) override;
+        // BarnesHut::RenderDebug (BarnesHut.cpp:98-101): one cube per occupied octree leaf, drawn with the
+        // reference's own Cube; like the reference, only when a D3D context was given.
+        void RenderDebug(DirectX::SimpleMath::Matrix view, DirectX::SimpleMath::Matrix proj) override;
 
         // INBodySim has no virtual destructor, so deleting through the base pointer never runs
         // ~B200Sim; owners that care about the device memory call Shutdown() first.
@@ -42,6 +46,8 @@ class B200Sim : public INBodySim
         nb_handle Handle = nullptr;
         EMode Mode;
         std::vector<Particle>* Particles = nullptr;
+        std::unique_ptr<Cube> DebugCube;
+        std::vector<float> DebugCells;
         void* Pinned = nullptr;
         size_t PinnedBytes = 0;
 

@@ -83,3 +83,35 @@ def test_adapter_barneshut_equals_reference_barneshut(pkg):
     assert np.median(err) < 1e-3
     assert np.median(rel_err(got["Forces"], want["Forces"])) < 1e-3     # BarnesHut leaves the last force in place
     assert np.abs(got["Position"] - want["Position"]).max() < 1e-3
+
+
+def debug_cubes(p, impl, dt, steps, theta=0.5):
+    lib = C.CDLL(LIB)
+    lib.adapter_debug_cubes.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_size_t]
+    lib.adapter_debug_cubes.restype = C.c_long
+    q = p.copy()
+    out = np.zeros((len(p), 4), dtype=np.float32)
+    k = lib.adapter_debug_cubes(q.ctypes.data, len(q), impl, dt, steps, theta, out.ctypes.data, len(out))
+    return k, out[:max(k, 0)]
+
+
+@needs_lib
+def test_reference_render_debug_draws_one_cube_per_occupied_leaf(pkg):
+    from oracle import ref
+    p = pkg.seed_galaxy_host(1024, 42, 1.0)
+    k, cubes = debug_cubes(p, REFERENCE, np.float32(0.02 / 60), 1)
+    want, _ = ref.octree_leaf_cubes(p)                           # the tree Update built: positions BEFORE the drift
+    assert k == len(want) and np.array_equal(cubes, want)
+
+
+@needs_lib
+@pytest.mark.gpu
+def test_adapter_render_debug_draws_the_reference_cubes(pkg):
+    """Sim->RenderDebug(view, proj) through INBodySim on both sims: same cubes in the same order."""
+    p = pkg.seed_galaxy_host(4096, 8, 1.0)
+    dt = np.float32(0.02 / 60)
+    k0, want = debug_cubes(p, REFERENCE, dt, 2)
+    k1, got = debug_cubes(p, B200, dt, 2)
+    assert k0 == k1 > 0
+    assert np.array_equal(got[:, 3], want[:, 3])
+    assert np.abs(got[:, :3] - want[:, :3]).max() <= 1e-3
