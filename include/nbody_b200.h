@@ -201,6 +201,10 @@ NB_API int nb_get_leaf_cells(nb_handle h, float* cells4, uint32_t* body, size_t*
 /* Counters of the last traversal summed over owned targets: {accepted cells, pair (leaf)
  * evaluations, node visits}. */
 NB_API int nb_get_walk_stats(nb_handle h, uint64_t stats3[3]);
+/* Profiling hook: lane occupancy of the instrumented traversal nb_get_walk_stats just ran --
+ * hist33[k] = warp iterations (node visits by a warp) during which k of the 32 lanes were at work
+ * (the others were parked inside a subtree they had accepted as a whole). */
+NB_API int nb_get_walk_occupancy(nb_handle h, uint64_t hist33[33]);
 /* Kinetic and potential energy of the conserved quantity of this force law,
  * E = sum 1/2 m v^2 + position_scale * sum_{i<j} U(r), U = -(G ma mb / sqrt(S)) atan(sqrt(S)/r),
  * potential by exact pair sum over owned targets x all sources (O(N^2/world)). */

@@ -106,6 +106,7 @@ def load():
     L.nb_get_morton.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_get_tree.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     L.nb_get_walk_stats.argtypes = [vp, vp]
+    L.nb_get_walk_occupancy.argtypes = [vp, vp]
     L.nb_get_leaf_cells.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_energy.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
     L.nb_energy_sampled.argtypes = [vp, sz, C.POINTER(f64), C.POINTER(f64), C.POINTER(sz)]
@@ -311,6 +312,12 @@ class Sim:
         s = np.zeros(3, dtype=np.uint64)
         _check(self._L.nb_get_walk_stats(self._h, s.ctypes.data))
         return dict(cell_evals=int(s[0]), leaf_evals=int(s[1]), visits=int(s[2]))
+
+    def walk_occupancy(self):
+        """Lane-occupancy histogram [0..32] of the traversal walk_stats() just ran."""
+        h = (C.c_uint64 * 33)()
+        _check(self._L.nb_get_walk_occupancy(self._h, h))
+        return np.array(list(h), dtype=np.uint64)
 
     def energy(self):
         ke, pe = C.c_double(), C.c_double()

@@ -36,6 +36,7 @@ namespace nb
 constexpr int kLevels = 21;
 constexpr unsigned long long kOutside = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kEnd = -1;
+constexpr int kWalkStatWords = 3 + 33;   // {cells, pairs, visits} + lane-occupancy histogram [0..32]
 
 // counters[] slots
 enum { C_INBOUNDS = 0, C_TOTAL = 1, C_WORDS = 8 };
@@ -625,6 +626,12 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
         ay = fmaf(s, dy, ay);
         az = fmaf(s, dz, az);
         if (use) parked = skip;
+        if (STATS)
+        {
+            // lane-occupancy histogram of the walk: stats[3 + k] counts warp iterations with k lanes at work
+            const unsigned int busy = __ballot_sync(0xffffffffu, active);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&stats[3 + __popc(busy)], 1ull);
+        }
         if (STATS && active)
         {
             ++n_visits;
@@ -817,8 +824,8 @@ int tree_reserve(nb_sim* h)
     NB_CUDA(cudaMalloc(&t.flags, n * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.nsum, 4 * n * sizeof(double)));
     NB_CUDA(cudaMalloc(&t.walk_a, 4 * n * sizeof(float4)));           // 2n records x 32 B
-    NB_CUDA(cudaMalloc(&t.stats, 3 * sizeof(unsigned long long)));
-    NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), h->stream));
+    NB_CUDA(cudaMalloc(&t.stats, kWalkStatWords * sizeof(unsigned long long)));
+    NB_CUDA(cudaMemsetAsync(t.stats, 0, kWalkStatWords * sizeof(unsigned long long), h->stream));
     t.capacity = n;
     return NB_OK;
 }
@@ -931,7 +938,7 @@ int tree_walk(nb_sim* h, bool balanced)
     const int group = h->cfg.kernel_variant == 1 ? 16 : (h->cfg.kernel_variant == 2 ? 8 : 32);
     if (g_walk_stats)
     {
-        NB_CUDA(cudaMemsetAsync(t.stats, 0, 3 * sizeof(unsigned long long), st));
+        NB_CUDA(cudaMemsetAsync(t.stats, 0, kWalkStatWords * sizeof(unsigned long long), st));
         NB_WALK(true, 32);
     }
     else if (group == 32) NB_WALK(false, 32);
@@ -1049,6 +1056,19 @@ int nb_get_walk_stats(nb_handle h, uint64_t stats3[3])
     unsigned long long s[3];
     NB_CUDA(cudaMemcpy(s, h->tree.stats, sizeof(s), cudaMemcpyDeviceToHost));
     stats3[0] = s[0]; stats3[1] = s[1]; stats3[2] = s[2];
+    return NB_OK;
+}
+
+int nb_get_walk_occupancy(nb_handle h, uint64_t hist33[33])
+{
+    NB_REQUIRE(h != nullptr && hist33 != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->cfg.mode == NB_MODE_BARNESHUT, NB_ERR_STATE, "handle is not in Barnes-Hut mode");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned long long s[kWalkStatWords];
+    NB_CUDA(cudaMemcpy(s, h->tree.stats, sizeof(s), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 33; ++k) hist33[k] = s[3 + k];
     return NB_OK;
 }
 

@@ -414,3 +414,14 @@ def test_leaf_cells_are_the_cubes_the_reference_draws(pkg):
         assert np.array_equal(again, cells)
         assert np.all(np.isfinite(sim.accelerations()))
         sim.close()
+
+
+def test_walk_occupancy_histogram_is_consistent_with_the_counters(pkg, galaxy):
+    """nb_get_walk_occupancy: sum_k k * hist[k] is the number of node visits by lanes that needed them."""
+    sim = bh(pkg, theta=0.5)
+    sim.init(galaxy)
+    st = sim.walk_stats()
+    h = sim.walk_occupancy()
+    assert int((h * np.arange(33, dtype=np.uint64)).sum()) == st["visits"]
+    assert h[0] == 0 and h.sum() >= st["visits"] // 32
+    sim.close()
