@@ -245,14 +245,15 @@ NB_API int nb_comm_init(nb_handle h, const uint8_t id[128]);
 NB_API int nb_device_posw(nb_handle h, void** dev_ptr, size_t* bytes);
 /* Fused exchange over NVLink peer memory (one process per GPU, one box): after nb_init_*, every rank
  * exports NB_P2P_HANDLE_BYTES opaque bytes (CUDA IPC handles of its two position buffers, its
- * flag array and its acceleration array), the launcher all-gathers them in rank order, every rank
+ * flag array, its acceleration array and the two arrays of the sorted Morton order), the launcher all-gathers them in rank order, every rank
  * attaches.  From then on the kick-drift kernel stores each new position directly into every rank's
  * position array and no collective is launched (csrc/p2p.cu); takes precedence over nb_comm_init.
  * In Barnes-Hut mode nb_step additionally balances the traversal: the Morton-ordered target list is
  * dealt out to the ranks block by block and every rank stores the accelerations it computed straight
- * into their owner's array. */
+ * into their owner's array, and shards the per-step sort: every rank sorts the bodies of one Morton-key
+ * range and stores its segment into every rank's sorted arrays. */
 #define NB_MAX_PEERS 16
-#define NB_P2P_HANDLE_BYTES 256
+#define NB_P2P_HANDLE_BYTES 384
 NB_API int nb_p2p_export(nb_handle h, uint8_t handles[NB_P2P_HANDLE_BYTES]);
 NB_API int nb_p2p_attach(nb_handle h, const uint8_t* all_handles /* world x NB_P2P_HANDLE_BYTES */);
 /* Same for handles that live in ONE process (peers[r] = the handle of rank r). */

@@ -362,7 +362,7 @@ class Sim:
         _check(self._L.nb_device_posw(self._h, C.byref(ptr), C.byref(nbytes)))
         return _CudaArray(ptr.value, nbytes.value, self)
 
-    P2P_HANDLE_BYTES = 256
+    P2P_HANDLE_BYTES = 384
 
     def p2p_export(self):
         buf = (C.c_uint8 * self.P2P_HANDLE_BYTES)()

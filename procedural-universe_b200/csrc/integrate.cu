@@ -162,4 +162,17 @@ int launch_pack_aos(nb_sim* h, size_t stride, bool forces_zero)
     return NB_OK;
 }
 
+// Forces the lazily loaded kernels of this file into the context (CUDA 12 loads a kernel at its first
+// launch, and that load can wait for the device to drain -- fatal if it happens while another handle of
+// the same process sits in a peer-flag wait; see p2p.cu).
+int preload_integrate()
+{
+    cudaFuncAttributes a;
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_kick_drift)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_reduce_partials)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_unpack_aos)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_pack_aos)));
+    return NB_OK;
+}
+
 }  // namespace nb

@@ -26,6 +26,7 @@ static int free_state(nb_sim* h)
     cudaFree(h->posw_buf[0]); cudaFree(h->posw_buf[1]);
     h->posw_buf[0] = h->posw_buf[1] = nullptr; h->posw = nullptr; h->posw_cur = 0;
     cudaFree(h->p2p_flags); h->p2p_flags = nullptr;
+    if (h->p2p_report) { cudaFreeHost(h->p2p_report); h->p2p_report = nullptr; }
     cudaFree(h->vel); h->vel = nullptr;
     cudaFree(h->mass); h->mass = nullptr;
     cudaFree(h->acc_base); h->acc_base = nullptr; h->acc = nullptr; h->acc_cur = 0; h->acc_two = false;
@@ -34,6 +35,15 @@ static int free_state(nb_sim* h)
     tree_release(h);
     h->n = h->first = h->count = 0;
     h->acc_valid = false;
+    return NB_OK;
+}
+
+int preload_allpairs(nb_sim* h)
+{
+    int count = 0;
+    const AllPairsKernel* table = allpairs_table(&count);
+    cudaFuncAttributes a;
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(table[h->ap_kernel].fn)));
     return NB_OK;
 }
 
@@ -135,7 +145,7 @@ static int compute_forces(nb_sim* h, bool timed, bool balanced = false)
     }
     else
     {
-        NB_CHECK(tree_build(h));
+        NB_CHECK(tree_build(h, balanced));
         if (timed) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
         NB_CHECK(tree_walk(h, balanced));
     }
@@ -419,7 +429,14 @@ int nb_host_unregister(void* ptr)
 int nb_sync(nb_handle h)
 {
     NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
-    NB_CUDA(cudaStreamSynchronize(h->stream));
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess)
+    {
+        char why[256];
+        if (p2p_describe_timeout(h, why, sizeof(why))) nb::set_error("nb_sync: %s (%s)", why, cudaGetErrorString(e));
+        else nb::set_error("nb_sync: %s", cudaGetErrorString(e));
+        return NB_ERR_CUDA;
+    }
     return NB_OK;
 }
 

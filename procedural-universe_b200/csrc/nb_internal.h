@@ -58,6 +58,12 @@ struct TreeBuffers
     int* rank = nullptr;            // [2n]  pre-order rank of every traversal record
     unsigned short* meta = nullptr; // [n-1] octree level of an internal node | 0x100 if it owns octree cells
     unsigned int* tlist = nullptr;  // [n]   owned targets in Morton order (world > 1)
+    unsigned long long* keys_final = nullptr;   // [n] sorted keys assembled from every rank's segment (p2p.cu)
+    unsigned int* vals_final = nullptr;         // [n]
+    unsigned long long* splitters = nullptr;    // [NB_MAX_PEERS + 1] first key of every rank's segment of the NEXT sort
+    const unsigned long long* skeys = nullptr;  // the sorted keys / body indices of the last build
+    const unsigned int* svals = nullptr;
+    bool dist_ready = false;        // splitters are valid: the next collective build may shard the sort
     int sort_bits_done = 0;
     int cur = 0;                    // which ping-pong half holds the sorted result
     size_t n_inbounds_host = 0;
@@ -125,7 +131,13 @@ struct nb_sim
     bool p2p_ipc = false;
     unsigned int p2p_step = 0;
     unsigned int p2p_acc_step = 0;
-    unsigned int* p2p_flags = nullptr;            // [2][NB_MAX_PEERS] step counters raised by the peers: positions, accelerations
+    unsigned int p2p_sort_step = 0;
+    // [4][NB_MAX_PEERS] step counters raised by the peers (positions, accelerations, sort counts, sort
+    // data), then [NB_MAX_PEERS] segment sizes of the sharded sort
+    unsigned int* p2p_flags = nullptr;
+    void* p2p_report = nullptr;                   // pinned host record written by a peer wait that timed out
+    void* peer_skeys[NB_MAX_PEERS] = {};
+    void* peer_svals[NB_MAX_PEERS] = {};
     void* peer_posw[2][NB_MAX_PEERS] = {};
     void* peer_flags[NB_MAX_PEERS] = {};
     void* peer_acc[NB_MAX_PEERS] = {};            // every rank's acc[3][count] (balanced Barnes-Hut walk)
@@ -140,11 +152,15 @@ int launch_unpack_aos(nb_sim* h, size_t stride, size_t begin, size_t end);
 int launch_reduce_partials(nb_sim* h);
 int launch_pack_aos(nb_sim* h, size_t stride, bool forces_zero);
 int choose_allpairs_config(nb_sim* h);
+int preload_integrate();
+int preload_tree();
+int preload_allpairs(nb_sim* h);
+int preload_step_kernels(nb_sim* h);
 
 // tree.cu
 int tree_reserve(nb_sim* h);
 void tree_release(nb_sim* h);
-int tree_build(nb_sim* h);
+int tree_build(nb_sim* h, bool collective = false);
 int tree_walk(nb_sim* h, bool balanced = false);
 
 // nccl_dl.cpp
@@ -160,6 +176,8 @@ int p2p_kick_drift_push(nb_sim* h, float dt);
 struct AccTable;
 int p2p_acc_table(const nb_sim* h, AccTable* out);
 int p2p_acc_exchange(nb_sim* h);
+bool p2p_describe_timeout(const nb_sim* h, char* out, size_t cap);
+int p2p_sort_exchange(nb_sim* h, const unsigned long long* keys_local, const unsigned int* vals_local, const unsigned int* count_dev);
 void p2p_release(nb_sim* h);
 
 // seed_host.cpp / seed_device.cu

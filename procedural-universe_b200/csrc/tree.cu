@@ -39,7 +39,7 @@ constexpr int kEnd = -1;
 constexpr int kWalkStatWords = 3 + 33;   // {cells, pairs, visits} + lane-occupancy histogram [0..32]
 
 // counters[] slots
-enum { C_INBOUNDS = 0, C_TOTAL = 1, C_WORDS = 8 };
+enum { C_INBOUNDS = 0, C_TOTAL = 1, C_SEG = 2, C_WORDS = 8 };   // C_SEG: bodies in this rank's key range (sharded sort)
 
 // ------------------------------------------------------------------------------------------------
 // K3: Morton codes.  Same cells as the comparison descent of the CPU restatement (oracle/nbody_port.c,
@@ -74,8 +74,17 @@ constexpr int MORTON_ITEMS = 4;   // bodies per thread: all loads are issued bef
 
 __global__ void __launch_bounds__(256)
 k_morton(const float4* __restrict__ posw, int n, double B, double cell, double inv_cell, unsigned long long* __restrict__ keys,
-         unsigned int* __restrict__ vals, unsigned int* __restrict__ counters)
+         unsigned int* __restrict__ vals, unsigned int* __restrict__ counters,
+         const unsigned long long* __restrict__ splitters, int seg, int nseg, unsigned int* __restrict__ in_segment)
 {
+    // sharded sort: in_segment[i] = 1 iff body i's key lies in this rank's key range [splitters[seg], splitters[seg+1])
+    // (the last range is open-ended and therefore also takes the out-of-bounds bodies, key ~0)
+    unsigned long long seg_lo = 0ull, seg_hi = 0ull;
+    if (in_segment != nullptr)
+    {
+        seg_lo = splitters[seg];
+        seg_hi = seg + 1 < nseg ? splitters[seg + 1] : 0ull;
+    }
     const int base = blockIdx.x * (256 * MORTON_ITEMS) + threadIdx.x;
     float4 p[MORTON_ITEMS];
 #pragma unroll
@@ -103,6 +112,7 @@ k_morton(const float4* __restrict__ posw, int n, double B, double cell, double i
             }
             keys[i] = key;
             vals[i] = (unsigned int)i;
+            if (in_segment != nullptr) in_segment[i] = (key >= seg_lo && (seg + 1 >= nseg || key < seg_hi)) ? 1u : 0u;
         }
     }
     // one atomic per block, not per warp: 16 M bodies would otherwise queue 512 K updates on one address
@@ -128,12 +138,16 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 
 __global__ void __launch_bounds__(RS_THREADS)
-k_rs_hist(const unsigned long long* __restrict__ keys, int n, int shift, unsigned int* __restrict__ hist, int tiles)
+k_rs_hist(const unsigned long long* __restrict__ keys, int n, int shift, unsigned int* __restrict__ hist, int tiles,
+          const unsigned int* __restrict__ n_dev)
 {
+    // n_dev: the key count lives on the device (sharded sort: this rank's segment); tiles past it are idle
+    if (n_dev != nullptr) n = (int)*n_dev;
+    const int base = blockIdx.x * RS_TILE;
+    if (base >= n) return;
     __shared__ unsigned int h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const int base = blockIdx.x * RS_TILE;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
     {
@@ -146,11 +160,13 @@ k_rs_hist(const unsigned long long* __restrict__ keys, int n, int shift, unsigne
 
 // one block per digit: in-place exclusive scan of the digit's row, total to totals[digit]
 __global__ void __launch_bounds__(256)
-k_rs_scan_rows(unsigned int* __restrict__ hist, int tiles, unsigned int* __restrict__ totals)
+k_rs_scan_rows(unsigned int* __restrict__ hist, int tiles, unsigned int* __restrict__ totals,
+               const unsigned int* __restrict__ n_dev = nullptr)
 {
     __shared__ unsigned int warp_sums[8];
     __shared__ unsigned int carry;
     unsigned int* row = hist + (size_t)blockIdx.x * tiles;
+    if (n_dev != nullptr) tiles = min(tiles, (int)((*n_dev + RS_TILE - 1) / RS_TILE));   // the row stride stays the full tile count
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (int base = 0; base < tiles; base += 256)
@@ -203,8 +219,11 @@ constexpr size_t RS_SCATTER_SMEM = RS_TILE * (sizeof(unsigned long long) + sizeo
 __global__ void __launch_bounds__(RS_THREADS, 3)
 k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
              unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
-             const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals, int tiles)
+             const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals, int tiles,
+             const unsigned int* __restrict__ n_dev)
 {
+    if (n_dev != nullptr) n = (int)*n_dev;
+    if (blockIdx.x * RS_TILE >= n) return;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(rs_smem);            // tile, input order
     unsigned int* svals = reinterpret_cast<unsigned int*>(skeys + RS_TILE);
@@ -782,6 +801,59 @@ k_compact(const unsigned int* __restrict__ flag, int n, const unsigned int* __re
     }
 }
 
+// Sharded sort, step 1: this rank's bodies (in_segment == 1) compacted in body order -- stable, so equal
+// keys keep their body order through the local sort exactly as in the full sort.  The last block leaves
+// the segment size in counters[C_SEG].
+__global__ void __launch_bounds__(256)
+k_compact_pairs(const unsigned int* __restrict__ flag, int n, const unsigned int* __restrict__ block_prefix,
+                const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+                unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, unsigned int* __restrict__ counters)
+{
+    __shared__ unsigned int warp_sums[8];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = block_prefix[blockIdx.x];
+    __syncthreads();
+    const int base = blockIdx.x * 4096;
+    for (int k = 0; k < 16; ++k)
+    {
+        const int i = base + k * 256 + threadIdx.x;
+        const unsigned int v = i < n ? flag[i] : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        unsigned int wprefix = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += warp_sums[w];
+        const unsigned int c = carry;
+        if (v)
+        {
+            const unsigned int at = c + wprefix + x - 1;
+            keys_out[at] = keys_in[i];
+            vals_out[at] = vals_in[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c + wprefix + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) counters[C_SEG] = carry;
+}
+
+// Key ranges of the NEXT sharded sort: equal shares of this step's in-bounds bodies.  Every rank holds the
+// same sorted keys, so every rank derives the same splitters.
+__global__ void k_splitters(const unsigned long long* __restrict__ skeys, const unsigned int* __restrict__ counters, int world,
+                            unsigned long long* __restrict__ splitters)
+{
+    const int r = threadIdx.x;
+    if (r > world) return;
+    const unsigned int m = counters[C_INBOUNDS];
+    splitters[r] = (r == 0 || m == 0) ? 0ull : (r == world ? kOutside : skeys[(size_t)r * m / world]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -794,6 +866,7 @@ void tree_release(nb_sim* h)
     cudaFree(t.hist); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
     cudaFree(t.range); cudaFree(t.flags); cudaFree(t.nsum); cudaFree(t.walk_a);
     cudaFree(t.walk_b); cudaFree(t.stats); cudaFree(t.cnt); cudaFree(t.pref); cudaFree(t.rank); cudaFree(t.tlist); cudaFree(t.meta);
+    cudaFree(t.keys_final); cudaFree(t.vals_final); cudaFree(t.splitters);
     t = TreeBuffers();
 }
 
@@ -801,6 +874,16 @@ int tree_reserve(nb_sim* h)
 {
     TreeBuffers& t = h->tree;
     const size_t n = h->n;
+    // Opt in to > 48 KB of dynamic shared memory once per device, here (Init time) and not in the step:
+    // the call can wait for the device to drain, which must never happen while another handle of this
+    // process sits in a peer-flag wait (several ranks driven by one host thread).
+    static bool opted_in[64] = {};
+    const int dev = h->cfg.device;
+    if (dev < 0 || dev >= 64 || !opted_in[dev])
+    {
+        NB_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+        if (dev >= 0 && dev < 64) opted_in[dev] = true;
+    }
     if (t.capacity >= n) return NB_OK;
     tree_release(h);
     const size_t tiles = (n + RS_TILE - 1) / RS_TILE;
@@ -830,47 +913,78 @@ int tree_reserve(nb_sim* h)
     return NB_OK;
 }
 
-int tree_build(nb_sim* h)
+int tree_build(nb_sim* h, bool collective)
 {
     NB_CHECK(tree_reserve(h));
     TreeBuffers& t = h->tree;
     const int n = (int)h->n;
     const int tiles = (n + RS_TILE - 1) / RS_TILE;
     cudaStream_t st = h->stream;
+    // collective: called from nb_step with peer memory attached, i.e. every rank is building right now.
+    // From the second such build on the sort is sharded by Morton-key range (splitters from the last one).
+    const bool peers = collective && h->p2p_attached && h->cfg.world > 1 && t.keys_final != nullptr;
+    const bool sharded = peers && t.dist_ready;
 
     NB_CUDA(cudaMemsetAsync(t.counters, 0, C_WORDS * sizeof(unsigned int), st));
     const double cell = std::ldexp((double)h->cfg.bounds, 1 - kLevels);      // 2B / 2^21, exact
-    k_morton<<<blocks_for(n, 256 * MORTON_ITEMS), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, cell, 1.0 / cell, t.keys[0], t.vals[0], t.counters);
+    k_morton<<<blocks_for(n, 256 * MORTON_ITEMS), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, cell, 1.0 / cell, t.keys[0], t.vals[0],
+                                                               t.counters, t.splitters, h->cfg.rank, h->cfg.world,
+                                                               sharded ? t.flags : nullptr);
     ++h->last_launches;
 
     unsigned int* totals = t.hist + (size_t)256 * tiles;
-    static bool smem_opt_in = false;
-    if (!smem_opt_in)
-    {
-        NB_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
-        smem_opt_in = true;
-    }
     int src = 0;
+    const unsigned int* n_dev = nullptr;
+    if (sharded)
+    {
+        // this rank's key range, compacted in body order into the second buffer: flags -> block sums -> scan -> pairs
+        const int blocks = (n + 4095) / 4096;
+        unsigned int* sums = t.hist;                  // scratch until the first histogram pass
+        k_block_sums<<<blocks, 256, 0, st>>>(t.flags, n, sums);
+        k_rs_scan_rows<<<1, 256, 0, st>>>(sums, blocks, sums + blocks);
+        k_compact_pairs<<<blocks, 256, 0, st>>>(t.flags, n, sums, t.keys[0], t.vals[0], t.keys[1], t.vals[1], t.counters);
+        h->last_launches += 3;
+        src = 1;
+        n_dev = t.counters + C_SEG;
+    }
     for (int pass = 0; pass < 8; ++pass)
     {
         const int shift = 8 * pass;
-        k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], n, shift, t.hist, tiles);
-        k_rs_scan_rows<<<256, 256, 0, st>>>(t.hist, tiles, totals);
+        k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], n, shift, t.hist, tiles, n_dev);
+        k_rs_scan_rows<<<256, 256, 0, st>>>(t.hist, tiles, totals, n_dev);
         k_rs_scan_totals<<<1, 256, 0, st>>>(totals);
         k_rs_scatter<<<tiles, RS_THREADS, RS_SCATTER_SMEM, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, shift,
-                                                                t.hist, totals, tiles);
+                                                                t.hist, totals, tiles, n_dev);
         h->last_launches += 4;
         src ^= 1;
     }
     t.cur = src;
     NB_CUDA(cudaGetLastError());
+    if (sharded)
+    {
+        // every rank's sorted segment -> every rank's final arrays, at its offset (p2p.cu)
+        NB_CHECK(p2p_sort_exchange(h, t.keys[src], t.vals[src], t.counters + C_SEG));
+        t.skeys = t.keys_final;
+        t.svals = t.vals_final;
+    }
+    else
+    {
+        t.skeys = t.keys[src];
+        t.svals = t.vals[src];
+    }
+    if (peers)
+    {
+        k_splitters<<<1, 32, 0, st>>>(t.skeys, t.counters, h->cfg.world, t.splitters);
+        ++h->last_launches;
+        t.dist_ready = true;
+    }
 
     const int leaf_base = n;
     const int words = n + 1;
     NB_CUDA(cudaMemsetAsync(t.cnt, 0, (size_t)words * sizeof(unsigned int), st));
-    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.keys[src], t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range,
+    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.skeys, t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range,
                                                 t.meta, t.cnt);
-    k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.parent, t.flags, t.nsum);
+    k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.svals, t.counters, leaf_base, t.child, t.parent, t.flags, t.nsum);
     // pre-order ranks: owning nodes per first slot were counted by k_karras; exclusive scan, rank, then the records
     {
         const int sblocks = (words + 4095) / 4096;
@@ -882,7 +996,7 @@ int tree_build(nb_sim* h)
         k_rank<<<blocks_for(n, 256), 256, 0, st>>>(t.counters, n, leaf_base, t.child, t.meta, t.parent, t.range, t.pref, t.rank);
         h->last_launches += 4;
     }
-    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.vals[src], t.counters, leaf_base, t.child, t.meta,
+    k_finalize<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.svals, t.counters, leaf_base, t.child, t.meta,
                                                   t.parent, t.nsum, 2.0f * h->cfg.bounds, 1.0f / h->cfg.theta, t.rank, t.walk_a);
     h->last_launches += 3;
     NB_CUDA(cudaGetLastError());
@@ -897,7 +1011,7 @@ int tree_walk(nb_sim* h, bool balanced)
     TreeBuffers& t = h->tree;
     const int n = (int)h->n;
     cudaStream_t st = h->stream;
-    const unsigned int* order = t.vals[t.cur];
+    const unsigned int* order = t.svals;
     const float sc = (float)(h->cfg.softening * (double)kPreScale);
     AccTable owners;
     std::memset(&owners, 0, sizeof(owners));
@@ -950,6 +1064,36 @@ int tree_walk(nb_sim* h, bool balanced)
     return NB_OK;
 }
 
+// Forces the lazily loaded kernels of this file into the context (CUDA 12 loads a kernel at its first
+// launch, and that load can wait for the device to drain -- fatal if it happens while another handle of
+// the same process sits in a peer-flag wait; see p2p.cu).
+int preload_tree()
+{
+    cudaFuncAttributes a;
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_morton)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_hist)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_rows)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_totals)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_karras)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_bottom_up)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_scan_apply)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rank)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_finalize)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk<false, 32, false>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk<false, 32, true>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk<false, 16, false>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk<false, 8, false>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk<true, 32, false>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_leaf_cells)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_select_flags)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_block_sums)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_compact)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_compact_pairs)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_splitters)));
+    return NB_OK;
+}
+
 }  // namespace nb
 
 using namespace nb;
@@ -967,8 +1111,8 @@ int nb_get_morton(nb_handle h, uint64_t* codes, uint32_t* order, size_t* n_inbou
     unsigned int m = 0;
     NB_CUDA(cudaMemcpy(&m, h->tree.counters + C_INBOUNDS, sizeof(m), cudaMemcpyDeviceToHost));
     if (n_inbounds) *n_inbounds = m;
-    if (codes) NB_CUDA(cudaMemcpy(codes, h->tree.keys[h->tree.cur], (size_t)m * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    if (order) NB_CUDA(cudaMemcpy(order, h->tree.vals[h->tree.cur], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (codes) NB_CUDA(cudaMemcpy(codes, h->tree.skeys, (size_t)m * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (order) NB_CUDA(cudaMemcpy(order, h->tree.svals, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return NB_OK;
 }
 
@@ -1029,13 +1173,13 @@ int nb_get_leaf_cells(nb_handle h, float* cells4, uint32_t* body, size_t* n_inbo
     if (cells4)
     {
         float4* d = t.walk_a;      // scratch: the traversal records are rewritten by every tree_build before a walk reads them
-        k_leaf_cells<<<blocks_for(m, 256), 256, 0, h->stream>>>(t.keys[t.cur], t.counters, (double)h->cfg.bounds, d);
+        k_leaf_cells<<<blocks_for(m, 256), 256, 0, h->stream>>>(t.skeys, t.counters, (double)h->cfg.bounds, d);
         NB_CUDA(cudaGetLastError());
         NB_CUDA(cudaMemcpyAsync(cells4, d, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
         NB_CUDA(cudaStreamSynchronize(h->stream));
         ++h->total_launches;
     }
-    if (body) NB_CUDA(cudaMemcpy(body, t.vals[t.cur], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (body) NB_CUDA(cudaMemcpy(body, t.svals, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return NB_OK;
 }
 

@@ -75,7 +75,7 @@ def connect(sim, rank):
 
 def connect_p2p(sim, rank, world):
     """Fused kick-drift + exchange over NVLink peer memory: all-gather the CUDA IPC handles in rank
-    order (torch.distributed carries 256 opaque bytes per rank), then attach."""
+    order (torch.distributed carries 384 opaque bytes per rank), then attach."""
     import torch.distributed as dist
     mine = sim.p2p_export()
     handles = [None] * world

@@ -274,6 +274,27 @@ def test_balanced_walk_over_peer_memory_reproduces_single_gpu_bitwise(pkg):
     assert np.array_equal(got["Forces"], want["Forces"])          # BarnesHut leaves m*a of the last step
     acc = np.concatenate([s.accelerations() for s in shards])
     assert np.array_equal(acc, one.accelerations())
+    # from the second step on the per-step sort is sharded by Morton-key range: every rank sorts one range
+    # and stores its segment into every rank's sorted arrays -- the same codes in the same order everywhere
+    codes, order = one.morton()
+    for s in shards:
+        c, o = s.morton()
+        assert np.array_equal(c, codes) and np.array_equal(o, order)
+    # a coarse step throws most arm bodies out of the cube: the key ranges of the previous step no longer
+    # balance (one rank's range may even be empty) and the result must not care
+    for _ in range(4):
+        one.step(0.05, 1)
+        for s in shards:
+            s.step(0.05, 1)
+    for s in shards:
+        s.read(got)
+    one.read(want)
+    assert np.array_equal(got["Position"], want["Position"]) and np.array_equal(got["Velocity"], want["Velocity"])
+    codes, order = one.morton()
+    assert len(codes) < len(p) // 2                              # most bodies have left
+    for s in shards:
+        c, o = s.morton()
+        assert np.array_equal(c, codes) and np.array_equal(o, order)
     for s in shards:
         s.close()
     one.close()
