@@ -37,8 +37,9 @@ struct PeerTable
 
 // rows of the flag array; the segment sizes of the sharded sort follow the rows
 enum { ROW_POS = 0, ROW_ACC = 1, ROW_SORT_COUNT = 2, ROW_SORT_DATA = 3, FLAG_ROWS = 4 };
-constexpr int kFlagWords = (FLAG_ROWS + 1) * NB_MAX_PEERS;
-constexpr int kSegCountAt = FLAG_ROWS * NB_MAX_PEERS;
+constexpr int kFlagWords = (FLAG_ROWS + 2) * NB_MAX_PEERS;
+constexpr int kSegCountAt = FLAG_ROWS * NB_MAX_PEERS;          // bodies every rank sorted this step ...
+constexpr int kSegOobAt = (FLAG_ROWS + 1) * NB_MAX_PEERS;      // ... and how many of them lie outside the cube
 
 __global__ void __launch_bounds__(256)
 k_kick_drift_push(PeerTable pt, int cur, int first, int count, double* __restrict__ vel,
@@ -282,16 +283,19 @@ int p2p_acc_exchange(nb_sim* h)
 }
 
 // ---- sharded sort of the Barnes-Hut build -------------------------------------------------------
-// Every rank has sorted the bodies whose Morton key falls into ITS key range (tree.cu).  The ranges
-// tile the key space in rank order, so the global sorted array is the concatenation of the segments:
-// (1) every rank tells every rank its segment size, (2) every rank stores its segment at its offset
-// into every rank's final arrays.  No collective is launched; the bytes cross NVLink as plain stores.
+// Every rank has sorted the in-bounds bodies whose Morton key falls into ITS key range plus the
+// out-of-bounds bodies (key ~0) of ITS index range (tree.cu); locally the latter sort to the end, in body
+// order.  The key ranges tile the key space in rank order, so the global sorted array is
+//     [in-bounds part of rank 0] ... [in-bounds part of rank P-1] [out-of-bounds part of rank 0] ... [of rank P-1]:
+// (1) every rank tells every rank its two sizes, (2) every rank stores its two parts at their offsets into
+// every rank's final arrays.  No collective is launched; the bytes cross NVLink as plain stores.
 __global__ void k_publish_count(PeerTable pt, const unsigned int* __restrict__ count_dev, unsigned int step)
 {
     const int r = threadIdx.x;
     if (r < pt.world)
     {
-        pt.flags[r][kSegCountAt + pt.rank] = *count_dev;
+        pt.flags[r][kSegCountAt + pt.rank] = count_dev[0];
+        pt.flags[r][kSegOobAt + pt.rank] = count_dev[1];
         __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pt.flags[r] + ROW_SORT_COUNT * NB_MAX_PEERS + pt.rank), "r"(step) : "memory");
     }
@@ -301,19 +305,26 @@ __global__ void __launch_bounds__(256)
 k_push_segment(PeerTable pt, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ vals,
                const unsigned int* seg_count /* my copy of every rank's segment size */)
 {
-    unsigned int off = 0;
-    for (int q = 0; q < pt.rank; ++q) off += seg_count[q];
-    const unsigned int cnt = seg_count[pt.rank];
+    const unsigned int* seg_oob = seg_count + (kSegOobAt - kSegCountAt);
+    unsigned int inb_before = 0, inb_all = 0, oob_before = 0;
+    for (int q = 0; q < pt.world; ++q)
+    {
+        const unsigned int inb = seg_count[q] - seg_oob[q];
+        if (q < pt.rank) { inb_before += inb; oob_before += seg_oob[q]; }
+        inb_all += inb;
+    }
+    const unsigned int cnt = seg_count[pt.rank], inb_mine = cnt - seg_oob[pt.rank];
     for (unsigned int j = blockIdx.x * 256u + threadIdx.x; j < cnt; j += gridDim.x * 256u)
     {
         const unsigned long long k = keys[j];
         const unsigned int v = vals[j];
+        const unsigned int at = j < inb_mine ? inb_before + j : inb_all + oob_before + (j - inb_mine);
 #pragma unroll 1
         for (int r = 0; r < pt.world; ++r)
         {
             const int dst = (pt.rank + r) % pt.world;
-            pt.skeys[dst][off + j] = k;
-            pt.svals[dst][off + j] = v;
+            pt.skeys[dst][at] = k;
+            pt.svals[dst][at] = v;
         }
     }
 }

@@ -39,7 +39,7 @@ constexpr int kEnd = -1;
 constexpr int kWalkStatWords = 3 + 33;   // {cells, pairs, visits} + lane-occupancy histogram [0..32]
 
 // counters[] slots
-enum { C_INBOUNDS = 0, C_TOTAL = 1, C_SEG = 2, C_WORDS = 8 };   // C_SEG: bodies in this rank's key range (sharded sort)
+enum { C_INBOUNDS = 0, C_TOTAL = 1, C_SEG = 2, C_SEG_OOB = 3, C_WORDS = 8 };   // C_SEG: bodies this rank sorts (sharded sort), C_SEG_OOB: of which outside the cube
 
 // ------------------------------------------------------------------------------------------------
 // K3: Morton codes.  Same cells as the comparison descent of the CPU restatement (oracle/nbody_port.c,
@@ -75,10 +75,13 @@ constexpr int MORTON_ITEMS = 4;   // bodies per thread: all loads are issued bef
 __global__ void __launch_bounds__(256)
 k_morton(const float4* __restrict__ posw, int n, double B, double cell, double inv_cell, unsigned long long* __restrict__ keys,
          unsigned int* __restrict__ vals, unsigned int* __restrict__ counters,
-         const unsigned long long* __restrict__ splitters, int seg, int nseg, unsigned int* __restrict__ in_segment)
+         const unsigned long long* __restrict__ splitters, int seg, int nseg, unsigned int* __restrict__ in_segment,
+         int oob_first, int oob_count)
 {
-    // sharded sort: in_segment[i] = 1 iff body i's key lies in this rank's key range [splitters[seg], splitters[seg+1])
-    // (the last range is open-ended and therefore also takes the out-of-bounds bodies, key ~0)
+    // sharded sort: in_segment[i] = 1 iff this rank sorts body i -- an in-bounds body whose key lies in the rank's
+    // key range [splitters[seg], splitters[seg+1]) (the last range is open-ended), or an out-of-bounds body
+    // (key ~0, they all sort to the end in body order) of the rank's INDEX range [oob_first, oob_first + oob_count):
+    // after a dispersal most bodies are outside, and one rank must not end up sorting and shipping all of them.
     unsigned long long seg_lo = 0ull, seg_hi = 0ull;
     if (in_segment != nullptr)
     {
@@ -94,7 +97,7 @@ k_morton(const float4* __restrict__ posw, int n, double B, double cell, double i
         p[k] = i < n ? posw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float b = (float)B;
-    int inside_count = 0;
+    int inside_count = 0, oob_mine = 0;
 #pragma unroll
     for (int k = 0; k < MORTON_ITEMS; ++k)
     {
@@ -112,18 +115,30 @@ k_morton(const float4* __restrict__ posw, int n, double B, double cell, double i
             }
             keys[i] = key;
             vals[i] = (unsigned int)i;
-            if (in_segment != nullptr) in_segment[i] = (key >= seg_lo && (seg + 1 >= nseg || key < seg_hi)) ? 1u : 0u;
+            if (in_segment != nullptr)
+            {
+                const bool mine = inside ? (key >= seg_lo && (seg + 1 >= nseg || key < seg_hi))
+                                         : (i >= oob_first && i < oob_first + oob_count);
+                in_segment[i] = mine ? 1u : 0u;
+                oob_mine += (mine && !inside) ? 1 : 0;
+            }
         }
     }
     // one atomic per block, not per warp: 16 M bodies would otherwise queue 512 K updates on one address
-    __shared__ int block_count;
-    if (threadIdx.x == 0) block_count = 0;
+    __shared__ int block_count, block_oob;
+    if (threadIdx.x == 0) { block_count = 0; block_oob = 0; }
     __syncthreads();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) inside_count += __shfl_down_sync(0xffffffffu, inside_count, o);
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        inside_count += __shfl_down_sync(0xffffffffu, inside_count, o);
+        oob_mine += __shfl_down_sync(0xffffffffu, oob_mine, o);
+    }
     if ((threadIdx.x & 31) == 0 && inside_count) atomicAdd(&block_count, inside_count);
+    if ((threadIdx.x & 31) == 0 && oob_mine) atomicAdd(&block_oob, oob_mine);
     __syncthreads();
     if (threadIdx.x == 0 && block_count) atomicAdd(&counters[C_INBOUNDS], (unsigned int)block_count);
+    if (threadIdx.x == 0 && block_oob) atomicAdd(&counters[C_SEG_OOB], (unsigned int)block_oob);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -929,7 +944,7 @@ int tree_build(nb_sim* h, bool collective)
     const double cell = std::ldexp((double)h->cfg.bounds, 1 - kLevels);      // 2B / 2^21, exact
     k_morton<<<blocks_for(n, 256 * MORTON_ITEMS), 256, 0, st>>>(h->posw, n, (double)h->cfg.bounds, cell, 1.0 / cell, t.keys[0], t.vals[0],
                                                                t.counters, t.splitters, h->cfg.rank, h->cfg.world,
-                                                               sharded ? t.flags : nullptr);
+                                                               sharded ? t.flags : nullptr, (int)h->first, (int)h->count);
     ++h->last_launches;
 
     unsigned int* totals = t.hist + (size_t)256 * tiles;
@@ -963,7 +978,7 @@ int tree_build(nb_sim* h, bool collective)
     if (sharded)
     {
         // every rank's sorted segment -> every rank's final arrays, at its offset (p2p.cu)
-        NB_CHECK(p2p_sort_exchange(h, t.keys[src], t.vals[src], t.counters + C_SEG));
+        NB_CHECK(p2p_sort_exchange(h, t.keys[src], t.vals[src], t.counters + C_SEG));   // {total, out-of-bounds} = C_SEG, C_SEG_OOB
         t.skeys = t.keys_final;
         t.svals = t.vals_final;
     }
