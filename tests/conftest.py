@@ -11,6 +11,10 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# A peer-flag wait that can never be satisfied (a bug in the exchange protocol) must fail the test in
+# seconds, not after the library's 10-minute default (csrc/p2p.cu, k_wait).
+os.environ.setdefault("NB_P2P_TIMEOUT_MS", "30000")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
