@@ -180,10 +180,24 @@ NB_API int nb_num_bodies(nb_handle h, size_t* n);
 NB_API int nb_shard_range(size_t n, int rank, int world, size_t* first, size_t* count);
 
 /* ---- parity hooks --------------------------------------------------------------------------- */
-/* Accelerations (Forces / Mass of the reference) of the owned bodies for the CURRENT positions,
- * without integrating: acc3[3*count] doubles. */
+/* Accelerations (Forces / Mass of the reference) of the owned bodies for the CURRENT positions and
+ * theta, without integrating: acc3[3*count] doubles.  nb_get_accel evaluates them if no evaluation of
+ * the current positions exists (every nb_step / nb_init_* / nb_set_theta invalidates the last one). */
 NB_API int nb_compute_accel(nb_handle h);
 NB_API int nb_get_accel(nb_handle h, double* acc3);
+/* The same accelerations for a list of GLOBAL body indices (NaN for bodies this handle does not own):
+ * acc3[3*k].  At 16 M bodies nb_get_accel is a 400 MB read-back; parity checks want a few hundred. */
+NB_API int nb_get_accel_of(nb_handle h, const uint32_t* bodies, size_t k, double* acc3);
+/* Cross-check at any N: BruteForceCPU::Exec (BruteForceCPU.cpp:25-43) with Phys::Gravity (Physics.hpp:25-35)
+ * restated operation by operation on the device -- fp32 difference / DistanceSquared / Normalize without
+ * fusion, fp64 force and accumulation -- for the listed bodies (any bodies, owned or not) against ALL
+ * sources of the current positions.  O(k * N); independent of the handle's mode and of the fast kernels. */
+NB_API int nb_direct_accel(nb_handle h, const uint32_t* bodies, size_t k, double* acc3);
+/* 64-bit checksums of the device state: hash2[0] over {x, y, z, G m} of ALL n bodies (equal on every rank
+ * after an exchange, equal between runs iff the positions are bitwise equal), hash2[1] over the fp64
+ * velocities of the OWNED bodies, keyed by global body index so that the values of all ranks add up
+ * (mod 2^64) to the single-handle value. */
+NB_API int nb_state_hash(nb_handle h, uint64_t hash2[2]);
 /* Barnes-Hut topology of the last build: number of in-bounds bodies, their 63-bit Morton codes in
  * sorted order and the body index of each sorted slot (bodies outside the root cube are dropped
  * as sources, Octree.cpp:58-62). */
@@ -265,6 +279,10 @@ NB_API int nb_mark_exchanged(nb_handle h);
 /* Device time in milliseconds (CUDA events on the handle's stream) of the last nb_step call and of
  * its dominant kernel, and how many kernels that call launched. */
 NB_API int nb_last_step_timing(nb_handle h, float* total_ms, float* force_kernel_ms, int* launches);
+/* The same two figures averaged over the last `max_steps` force passes (at most 64 are kept; 0 = all kept):
+ * the library records three CUDA events per step on the handle's stream and reads them only here, so a
+ * timed loop needs no host synchronisation between steps. */
+NB_API int nb_step_timing_mean(nb_handle h, int max_steps, float* force_kernel_ms, float* build_ms, int* steps_averaged);
 /* Barnes-Hut: device time of the tree build (Morton + sort + Karras + reduction) of that step;
  * force_kernel_ms above is then the traversal alone.  0 in all-pairs mode. */
 NB_API int nb_last_build_timing(nb_handle h, float* build_ms);

@@ -106,6 +106,28 @@ def energy(p):
     return ke.value, pe.value
 
 
+def energy_sampled(p, stride, G=6.674e-11, S=10.0, scale=20 * 1.15e12):
+    """The estimator of nb_energy_sampled (csrc/energy.cu) restated in numpy: kinetic energy exactly,
+    potential from the bodies whose index is a multiple of `stride`, each against ALL sources, times `stride`:
+    E = sum 1/2 m v^2 + scale * sum_{i<j} U(r),  U = -(G ma mb / sqrt(S)) atan(sqrt(S) / r).
+    Returns (kinetic, potential estimate, samples)."""
+    pos = p["Position"].astype(np.float64)
+    m = p["Mass"]
+    ke = float(np.sum(0.5 * m * np.sum(p["Velocity"] ** 2, axis=1)))
+    w = (G * m).astype(np.float32).astype(np.float64)      # the device keeps G m_j in fp32
+    sq = np.sqrt(S)
+    pe = 0.0
+    idx = np.arange(0, len(p), stride)
+    for i in idx:
+        d = pos - pos[i]
+        r = np.sqrt(np.einsum("ij,ij->i", d, d))
+        with np.errstate(divide="ignore"):
+            a = np.where(r > 0.0, np.arctan(sq / r), np.pi / 2)
+        a[i] = 0.0
+        pe += 0.5 * m[i] / sq * float(-(w * a).sum())
+    return ke, pe * stride * scale, len(idx)
+
+
 def recentre(p):
     """InitParticlesFromFile's recentring (reference SimulationState.cpp:252-270) restated in numpy:
     TotalMass accumulates in `long double`, the weighted position sums in double, both in index

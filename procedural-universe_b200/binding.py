@@ -103,6 +103,9 @@ def load():
     L.nb_num_bodies.argtypes = [vp, C.POINTER(sz)]
     L.nb_compute_accel.argtypes = [vp]
     L.nb_get_accel.argtypes = [vp, vp]
+    L.nb_get_accel_of.argtypes = [vp, vp, sz, vp]
+    L.nb_direct_accel.argtypes = [vp, vp, sz, vp]
+    L.nb_state_hash.argtypes = [vp, vp]
     L.nb_get_morton.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_get_tree.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     L.nb_get_walk_stats.argtypes = [vp, vp]
@@ -123,6 +126,7 @@ def load():
     L.nb_p2p_attach.argtypes = [vp, vp]
     L.nb_p2p_attach_local.argtypes = [vp, C.POINTER(vp)]
     L.nb_last_step_timing.argtypes = [vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int)]
+    L.nb_step_timing_mean.argtypes = [vp, C.c_int, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int)]
     L.nb_probe_fp32_peak.argtypes = [vp, C.POINTER(f64)]
     L.nb_last_build_timing.argtypes = [vp, C.POINTER(f32)]
     L.nb_shard_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
@@ -282,11 +286,25 @@ class Sim:
         _check(self._L.nb_get_accel(self._h, acc.ctypes.data))
         return acc
 
-    def last_accelerations(self):
-        _, cnt = self.owned_range()
-        acc = np.zeros((cnt, 3), dtype=np.float64)
-        _check(self._L.nb_get_accel(self._h, acc.ctypes.data))
+    def accelerations_of(self, bodies):
+        """Accelerations (current positions) of the listed global body indices; NaN rows for bodies not owned."""
+        b = np.ascontiguousarray(bodies, dtype=np.uint32)
+        acc = np.zeros((len(b), 3), dtype=np.float64)
+        _check(self._L.nb_get_accel_of(self._h, b.ctypes.data, len(b), acc.ctypes.data))
         return acc
+
+    def direct_accelerations(self, bodies):
+        """The reference's all-pairs law restated on the device for the listed bodies x all sources."""
+        b = np.ascontiguousarray(bodies, dtype=np.uint32)
+        acc = np.zeros((len(b), 3), dtype=np.float64)
+        _check(self._L.nb_direct_accel(self._h, b.ctypes.data, len(b), acc.ctypes.data))
+        return acc
+
+    def state_hash(self):
+        """(checksum of all positions, checksum of the owned velocities)."""
+        h = np.zeros(2, dtype=np.uint64)
+        _check(self._L.nb_state_hash(self._h, h.ctypes.data))
+        return int(h[0]), int(h[1])
 
     def morton(self):
         codes = np.zeros(self.n, dtype=np.uint64)
@@ -386,6 +404,12 @@ class Sim:
         t, f, k = C.c_float(), C.c_float(), C.c_int()
         _check(self._L.nb_last_step_timing(self._h, C.byref(t), C.byref(f), C.byref(k)))
         return t.value, f.value, k.value
+
+    def step_timing_mean(self, max_steps=0):
+        """(dominant kernel ms, tree build ms, steps averaged) over the last force passes (<= 64 kept)."""
+        a, b, k = C.c_float(), C.c_float(), C.c_int()
+        _check(self._L.nb_step_timing_mean(self._h, max_steps, C.byref(a), C.byref(b), C.byref(k)))
+        return a.value, b.value, k.value
 
     def last_build_ms(self):
         t = C.c_float()

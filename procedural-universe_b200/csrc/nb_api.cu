@@ -130,26 +130,31 @@ int launch_allpairs(nb_sim* h)
     return NB_OK;
 }
 
-// `timed`: bracket the dominant kernel (all-pairs kernel / tree walk) with ev[2], ev[3] and the
-// tree build with ev[4], ev[2].
+// `timed`: bracket the force pass in the next slot of the event ring -- {pass begin, dominant kernel
+// (all-pairs kernel / tree walk) begin, dominant kernel end}; the tree build lies between the first two.
 // `balanced`: Barnes-Hut inside nb_step with peer memory attached -- every rank walks an interleaved
 // share of ALL targets and stores into the owners' arrays; the exchange that follows makes sure this
 // rank's own accelerations are complete before the kick-drift reads them.
 static int compute_forces(nb_sim* h, bool timed, bool balanced = false)
 {
-    if (timed) NB_CUDA(cudaEventRecord(h->ev[4], h->stream));
+    cudaEvent_t* slot = h->ring[h->ring_pos % NB_TIMING_RING];
+    if (timed) NB_CUDA(cudaEventRecord(slot[0], h->stream));
     if (h->cfg.mode == NB_MODE_ALLPAIRS)
     {
-        if (timed) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        if (timed) NB_CUDA(cudaEventRecord(slot[1], h->stream));
         NB_CHECK(launch_allpairs(h));
     }
     else
     {
         NB_CHECK(tree_build(h, balanced));
-        if (timed) NB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        if (timed) NB_CUDA(cudaEventRecord(slot[1], h->stream));
         NB_CHECK(tree_walk(h, balanced));
     }
-    if (timed) NB_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    if (timed)
+    {
+        NB_CUDA(cudaEventRecord(slot[2], h->stream));
+        ++h->ring_pos;
+    }
     if (balanced && h->cfg.mode == NB_MODE_BARNESHUT) NB_CHECK(p2p_acc_exchange(h));
     return NB_OK;
 }
@@ -264,9 +269,10 @@ int nb_create(const nb_config* cfg, nb_handle* out)
         if (e == cudaSuccess) e = cudaMemset(h->wmax, 0, sizeof(float));
         if (e != cudaSuccess) { nb::set_error("cudaMalloc: %s", cudaGetErrorString(e)); nb_destroy(h); return NB_ERR_CUDA; }
     }
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 2 + 3 * NB_TIMING_RING; ++i)
     {
-        cudaError_t e = cudaEventCreate(&h->ev[i]);
+        cudaEvent_t* slot = i < 2 ? &h->ev[i] : &h->ring[(i - 2) / 3][(i - 2) % 3];
+        cudaError_t e = cudaEventCreate(slot);
         if (e != cudaSuccess) { nb::set_error("cudaEventCreate: %s", cudaGetErrorString(e)); nb_destroy(h); return NB_ERR_CUDA; }
     }
     *out = h;
@@ -282,8 +288,11 @@ int nb_destroy(nb_handle h)
     free_state(h);
     cudaFree(h->d_aos);
     cudaFree(h->wmax);
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 2; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < NB_TIMING_RING; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (h->ring[i][k]) cudaEventDestroy(h->ring[i][k]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return NB_OK;
@@ -348,6 +357,9 @@ int nb_step(nb_handle h, float dt, int nsteps)
     NB_REQUIRE(h->n > 0, NB_ERR_STATE, "nb_init_* has not been called");
     NB_REQUIRE(nsteps >= 0, NB_ERR_ARG, "negative step count");
     NB_CUDA(cudaSetDevice(h->cfg.device));
+    // checked BEFORE anything is launched: a rank that integrated but could not exchange would diverge
+    NB_REQUIRE(h->p2p_attached || h->nccl_comm == nullptr || h->n % (size_t)h->cfg.world == 0, NB_ERR_ARG,
+               "the NCCL exchange needs the body count to be divisible by the number of ranks (use the peer-memory exchange for ragged shards)");
     h->last_launches = 0;
     h->timing_valid = false;
     NB_CUDA(cudaEventRecord(h->ev[0], h->stream));
@@ -355,9 +367,8 @@ int nb_step(nb_handle h, float dt, int nsteps)
     {
         NB_REQUIRE(h->exchanged, NB_ERR_STATE,
                    "world > 1 without nb_comm_init: call nb_mark_exchanged after exchanging positions");
-        const bool last = (s == nsteps - 1);
         if (h->p2p_attached) NB_CHECK(p2p_wait(h));          // every peer's positions of the last step are in
-        NB_CHECK(compute_forces(h, last, h->p2p_attached && h->cfg.world > 1 && h->cfg.mode == NB_MODE_BARNESHUT));
+        NB_CHECK(compute_forces(h, true, h->p2p_attached && h->cfg.world > 1 && h->cfg.mode == NB_MODE_BARNESHUT));
         h->acc_valid = false;
         h->forces_from_last_step = true;
         if (h->p2p_attached)
@@ -545,7 +556,9 @@ int nb_get_accel(nb_handle h, double* acc3)
     NB_REQUIRE(h != nullptr && acc3 != nullptr, NB_ERR_ARG, "null argument");
     NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
     NB_CUDA(cudaSetDevice(h->cfg.device));
-    if (!h->acc_valid && !h->forces_from_last_step) NB_CHECK(nb_compute_accel(h));
+    // acc_valid is cleared by every step, Init and theta change: what is returned always belongs to the
+    // CURRENT positions and theta (forces_from_last_step only decides what the Forces write-back holds)
+    if (!h->acc_valid) NB_CHECK(nb_compute_accel(h));
     NB_CUDA(cudaStreamSynchronize(h->stream));
     double* tmp = nullptr;
     NB_CUDA(cudaMallocHost(&tmp, 3 * h->count * sizeof(double)));
@@ -614,8 +627,37 @@ int nb_last_step_timing(nb_handle h, float* total_ms, float* force_kernel_ms, in
     NB_CUDA(cudaSetDevice(h->cfg.device));
     NB_CUDA(cudaEventSynchronize(h->ev[1]));
     if (total_ms) NB_CUDA(cudaEventElapsedTime(total_ms, h->ev[0], h->ev[1]));
-    if (force_kernel_ms) NB_CUDA(cudaEventElapsedTime(force_kernel_ms, h->ev[2], h->ev[3]));
+    if (force_kernel_ms)
+    {
+        NB_REQUIRE(h->ring_pos > 0, NB_ERR_STATE, "no timed force pass yet");
+        cudaEvent_t* slot = h->ring[(h->ring_pos - 1) % NB_TIMING_RING];
+        NB_CUDA(cudaEventElapsedTime(force_kernel_ms, slot[1], slot[2]));
+    }
     if (launches) *launches = h->last_launches;
+    return NB_OK;
+}
+
+int nb_step_timing_mean(nb_handle h, int max_steps, float* force_kernel_ms, float* build_ms, int* steps_averaged)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(h->timing_valid && h->ring_pos > 0, NB_ERR_STATE, "no timed call yet");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CUDA(cudaEventSynchronize(h->ev[1]));
+    unsigned long long k = h->ring_pos < (unsigned long long)NB_TIMING_RING ? h->ring_pos : (unsigned long long)NB_TIMING_RING;
+    if (max_steps > 0 && (unsigned long long)max_steps < k) k = (unsigned long long)max_steps;
+    double kernel = 0.0, build = 0.0;
+    for (unsigned long long i = 0; i < k; ++i)
+    {
+        cudaEvent_t* slot = h->ring[(h->ring_pos - 1 - i) % NB_TIMING_RING];
+        float a = 0.f, b = 0.f;
+        NB_CUDA(cudaEventElapsedTime(&a, slot[1], slot[2]));
+        NB_CUDA(cudaEventElapsedTime(&b, slot[0], slot[1]));
+        kernel += a;
+        build += b;
+    }
+    if (force_kernel_ms) *force_kernel_ms = (float)(kernel / (double)k);
+    if (build_ms) *build_ms = (float)(build / (double)k);
+    if (steps_averaged) *steps_averaged = (int)k;
     return NB_OK;
 }
 
@@ -625,7 +667,9 @@ int nb_last_build_timing(nb_handle h, float* build_ms)
     NB_REQUIRE(h->timing_valid, NB_ERR_STATE, "no timed call yet");
     NB_CUDA(cudaSetDevice(h->cfg.device));
     NB_CUDA(cudaEventSynchronize(h->ev[1]));
-    NB_CUDA(cudaEventElapsedTime(build_ms, h->ev[4], h->ev[2]));
+    NB_REQUIRE(h->ring_pos > 0, NB_ERR_STATE, "no timed force pass yet");
+    cudaEvent_t* slot = h->ring[(h->ring_pos - 1) % NB_TIMING_RING];
+    NB_CUDA(cudaEventElapsedTime(build_ms, slot[0], slot[1]));
     return NB_OK;
 }
 

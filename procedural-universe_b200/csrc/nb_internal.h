@@ -84,6 +84,8 @@ struct AccTable
 };
 }  // namespace nb
 
+constexpr int NB_TIMING_RING = 64;
+
 struct nb_sim
 {
     nb_config cfg;
@@ -117,7 +119,11 @@ struct nb_sim
     bool forces_from_last_step = false;
     bool exchanged = true;       // posw of remote ranks is current
 
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // step begin/end, dominant kernel begin/end, force pass begin
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // begin / end of the last nb_step (or nb_compute_accel) call
+    // {force pass begin, dominant kernel begin, dominant kernel end} of the last NB_TIMING_RING force passes:
+    // recorded every step without a host sync, read back after the timed region (nb_step_timing_mean)
+    cudaEvent_t ring[NB_TIMING_RING][3] = {};
+    unsigned long long ring_pos = 0;          // force passes recorded so far
     bool timing_valid = false;
     int last_launches = 0;
     unsigned long long total_launches = 0;

@@ -79,6 +79,11 @@ int comm_init(nb_sim* h, const uint8_t id[128])
 {
     NcclApi& a = api();
     if (!a.ok) { set_error("libnccl.so.2 not found or incomplete"); return NB_ERR_NCCL; }
+    if (h->n > 0 && h->n % (size_t)h->cfg.world != 0)
+    {
+        set_error("nb_comm_init: the NCCL exchange needs the body count (%zu) to be divisible by the number of ranks (%d)", h->n, h->cfg.world);
+        return NB_ERR_ARG;
+    }
     if (h->nccl_comm != nullptr) comm_destroy(h);
     NcclUniqueId u;
     std::memcpy(u.internal, id, 128);
@@ -90,8 +95,8 @@ int comm_init(nb_sim* h, const uint8_t id[128])
 }
 
 // In-place all-gather: rank r contributes posw[first_r, first_r + count_r).  Requires equal shard
-// sizes (n divisible by world), which nb_comm_init's callers guarantee for the benchmark sizes;
-// ragged shards fall back to the host-driven exchange (nb_device_posw + nb_mark_exchanged).
+// sizes (n divisible by world): nb_comm_init and nb_step refuse anything else before a kernel is
+// launched.  Ragged shards use the peer-memory exchange (p2p.cu), which has no such constraint.
 int comm_allgather_posw(nb_sim* h)
 {
     NcclApi& a = api();

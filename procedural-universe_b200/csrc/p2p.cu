@@ -65,7 +65,9 @@ k_kick_drift_push(PeerTable pt, int cur, int first, int count, double* __restric
         ax = acc[i]; ay = acc[plane + i]; az = acc[2 * plane + i];
     }
     double vx = vel[i], vy = vel[plane + i], vz = vel[2 * plane + i];
-    vx += ax * dt; vy += ay * dt; vz += az * dt;
+    // Velocity += a * dt: a rounded product, then a rounded sum, as the reference's g++ build (-ffp-contract=off)
+    // computes it -- not a DFMA, which differs by an ulp every few steps
+    vx = __dadd_rn(vx, __dmul_rn(ax, dt)); vy = __dadd_rn(vy, __dmul_rn(ay, dt)); vz = __dadd_rn(vz, __dmul_rn(az, dt));
     vel[i] = vx; vel[plane + i] = vy; vel[2 * plane + i] = vz;
     float4 p = pt.posw[cur][pt.rank][first + i];
     p.x += (float)((vx * dt) / pos_scale);

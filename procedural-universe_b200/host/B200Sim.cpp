@@ -31,9 +31,13 @@ B200Sim::B200Sim(ID3D11DeviceContext* context, EMode mode, int device) : Mode(mo
 
     if (mode == EMode::BarnesHut)
     {
+        // BarnesHut.cpp:29-31: the handler writes the process-global Octree::Theta (so sims created
+        // later start from it) and this sim follows.
         EventStream::Register(EEvent::BHThetaChanged, [this](const EventData& data) {
-            SetTheta(EventValue<FloatEventData>(data));
+            Octree::Theta = EventValue<FloatEventData>(data);
+            SetTheta(static_cast<float>(Octree::Theta));
         });
+        ThetaRegistered = true;
     }
 }
 
@@ -44,6 +48,12 @@ B200Sim::~B200Sim()
 
 void B200Sim::Shutdown()
 {
+    // BarnesHut::~BarnesHut (BarnesHut.cpp:34-37): drop the BHThetaChanged handler, which captures `this`
+    if (ThetaRegistered)
+    {
+        EventStream::UnregisterAll(EEvent::BHThetaChanged);
+        ThetaRegistered = false;
+    }
     Unpin();
     if (Handle)
     {

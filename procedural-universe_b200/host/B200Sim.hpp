@@ -50,6 +50,7 @@ class B200Sim : public INBodySim
         std::vector<float> DebugCells;
         void* Pinned = nullptr;
         size_t PinnedBytes = 0;
+        bool ThetaRegistered = false;
 
         void Pin();
         void Unpin();
