@@ -188,6 +188,12 @@ NB_API int nb_get_accel(nb_handle h, double* acc3);
 /* The same accelerations for a list of GLOBAL body indices (NaN for bodies this handle does not own):
  * acc3[3*k].  At 16 M bodies nb_get_accel is a 400 MB read-back; parity checks want a few hundred. */
 NB_API int nb_get_accel_of(nb_handle h, const uint32_t* bodies, size_t k, double* acc3);
+/* The accelerations the LAST nb_step applied in its kick (Forces / Mass of that Update: evaluated at that
+ * step's PRE-drift positions), for a list of global body indices -- what the Forces write-back of
+ * nb_update_aos carries, without the 104-byte-per-body read-back.  After the first step of a run these are
+ * the accelerations of the initial conditions at no extra force pass (one all-pairs pass over 16 M bodies
+ * is 110 s on two GPUs).  NB_ERR_STATE before the first step. */
+NB_API int nb_get_step_accel_of(nb_handle h, const uint32_t* bodies, size_t k, double* acc3);
 /* Cross-check at any N: BruteForceCPU::Exec (BruteForceCPU.cpp:25-43) with Phys::Gravity (Physics.hpp:25-35)
  * restated operation by operation on the device -- fp32 difference / DistanceSquared / Normalize without
  * fusion, fp64 force and accumulation -- for the listed bodies (any bodies, owned or not) against ALL

@@ -104,6 +104,7 @@ def load():
     L.nb_compute_accel.argtypes = [vp]
     L.nb_get_accel.argtypes = [vp, vp]
     L.nb_get_accel_of.argtypes = [vp, vp, sz, vp]
+    L.nb_get_step_accel_of.argtypes = [vp, vp, sz, vp]
     L.nb_direct_accel.argtypes = [vp, vp, sz, vp]
     L.nb_state_hash.argtypes = [vp, vp]
     L.nb_get_morton.argtypes = [vp, vp, vp, C.POINTER(sz)]
@@ -291,6 +292,13 @@ class Sim:
         b = np.ascontiguousarray(bodies, dtype=np.uint32)
         acc = np.zeros((len(b), 3), dtype=np.float64)
         _check(self._L.nb_get_accel_of(self._h, b.ctypes.data, len(b), acc.ctypes.data))
+        return acc
+
+    def step_accelerations_of(self, bodies):
+        """Accelerations the LAST step applied (at its pre-drift positions) of the listed global body indices."""
+        b = np.ascontiguousarray(bodies, dtype=np.uint32)
+        acc = np.zeros((len(b), 3), dtype=np.float64)
+        _check(self._L.nb_get_step_accel_of(self._h, b.ctypes.data, len(b), acc.ctypes.data))
         return acc
 
     def direct_accelerations(self, bodies):

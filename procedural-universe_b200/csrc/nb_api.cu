@@ -184,6 +184,7 @@ static int set_bodies(nb_sim* h, size_t n)
     NB_CHECK(choose_allpairs_config(h));
     h->acc_valid = false;
     h->forces_from_last_step = false;
+    h->acc_is_last_step = false;
     h->exchanged = true;
     return NB_OK;
 }
@@ -371,6 +372,7 @@ int nb_step(nb_handle h, float dt, int nsteps)
         NB_CHECK(compute_forces(h, true, h->p2p_attached && h->cfg.world > 1 && h->cfg.mode == NB_MODE_BARNESHUT));
         h->acc_valid = false;
         h->forces_from_last_step = true;
+        h->acc_is_last_step = true;
         if (h->p2p_attached)
         {
             NB_CHECK(p2p_kick_drift_push(h, dt));            // ONE kernel: integrate + store into every rank
@@ -547,6 +549,7 @@ int nb_compute_accel(nb_handle h)
     NB_CUDA(cudaEventRecord(h->ev[1], h->stream));
     h->timing_valid = true;
     h->acc_valid = true;
+    h->acc_is_last_step = false;
     h->total_launches += (unsigned long long)h->last_launches;
     return NB_OK;
 }

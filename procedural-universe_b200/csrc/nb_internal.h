@@ -117,6 +117,7 @@ struct nb_sim
     int ap_splits = 1;
     bool acc_valid = false;
     bool forces_from_last_step = false;
+    bool acc_is_last_step = false;   // h->acc still holds what the last nb_step kicked with (no nb_compute_accel since)
     bool exchanged = true;       // posw of remote ranks is current
 
     cudaEvent_t ev[2] = {nullptr, nullptr};   // begin / end of the last nb_step (or nb_compute_accel) call

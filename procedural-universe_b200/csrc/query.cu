@@ -213,12 +213,9 @@ extern "C" int nb_direct_accel(nb_handle h, const uint32_t* bodies, size_t k, do
     return NB_OK;
 }
 
-extern "C" int nb_get_accel_of(nb_handle h, const uint32_t* bodies, size_t k, double* acc3)
+// acc planes of the owned range -> acc3[k][3] for the listed global body indices
+static int gather_accel(nb_handle h, const uint32_t* bodies, size_t k, double* acc3)
 {
-    NB_REQUIRE(h != nullptr && bodies != nullptr && acc3 != nullptr && k > 0, NB_ERR_ARG, "null argument");
-    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
-    NB_CUDA(cudaSetDevice(h->cfg.device));
-    if (!h->acc_valid) NB_CHECK(nb_compute_accel(h));
     unsigned int* d_idx = nullptr;
     double* d_out = nullptr;
     cudaError_t e = cudaMalloc(&d_idx, k * sizeof(unsigned int));
@@ -236,6 +233,24 @@ extern "C" int nb_get_accel_of(nb_handle h, const uint32_t* bodies, size_t k, do
     NB_CUDA(e);
     ++h->total_launches;
     return NB_OK;
+}
+
+extern "C" int nb_get_accel_of(nb_handle h, const uint32_t* bodies, size_t k, double* acc3)
+{
+    NB_REQUIRE(h != nullptr && bodies != nullptr && acc3 != nullptr && k > 0, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->acc_valid) NB_CHECK(nb_compute_accel(h));
+    return gather_accel(h, bodies, k, acc3);
+}
+
+extern "C" int nb_get_step_accel_of(nb_handle h, const uint32_t* bodies, size_t k, double* acc3)
+{
+    NB_REQUIRE(h != nullptr && bodies != nullptr && acc3 != nullptr && k > 0, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_REQUIRE(h->acc_is_last_step, NB_ERR_STATE, "no nb_step since the last nb_init_* / nb_compute_accel");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    return gather_accel(h, bodies, k, acc3);
 }
 
 extern "C" int nb_state_hash(nb_handle h, uint64_t hash2[2])
