@@ -321,6 +321,12 @@ class Sim:
         _check(self._L.nb_get_morton(self._h, codes.ctypes.data, order.ctypes.data, C.byref(m)))
         return codes[: m.value], order[: m.value]
 
+    def inbounds(self):
+        """Bodies inside the root cube at the last tree build (the others are dropped as sources, Octree.cpp:58-62)."""
+        m = C.c_size_t()
+        _check(self._L.nb_get_morton(self._h, None, None, C.byref(m)))
+        return m.value
+
     def tree(self):
         m = C.c_size_t()
         _check(self._L.nb_get_tree(self._h, None, None, None, None, None, C.byref(m)))

@@ -1206,6 +1206,7 @@ int nb_get_walk_stats(nb_handle h, uint64_t stats3[3])
     NB_CUDA(cudaSetDevice(h->cfg.device));
     // one instrumented traversal of the current tree (the production walk carries no counters)
     NB_REQUIRE(h->exchanged, NB_ERR_STATE, "positions of remote ranks are stale");
+    if (h->p2p_attached) NB_CHECK(p2p_wait(h));      // the peers' positions of the last step are in
     NB_CHECK(tree_build(h));
     g_walk_stats = true;
     const int rc = tree_walk(h);
