@@ -257,9 +257,21 @@ class Ctx:
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+        # NB_BENCH_ONE_DEVICE=1 (debugging the multi-process logic on a one-GPU box): every rank uses device 0 and
+        # torch.distributed runs on gloo; the library's peer-memory path (CUDA IPC) is the same
+        self.one_device = os.environ.get("NB_BENCH_ONE_DEVICE") == "1"
+        if self.one_device:
+            self.local_rank = 0
         torch.cuda.set_device(self.local_rank)
+        # a flag wait that can never be satisfied should end the run in minutes, not after the library's default
+        os.environ.setdefault("NB_P2P_TIMEOUT_MS", "120000")
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            import datetime
+            if self.one_device:
+                dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=600))
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank), timeout=datetime.timedelta(seconds=600))
+        self.cdev = "cpu" if self.one_device else "cuda"
         self.pkg = importlib.import_module("procedural-universe_b200")
         self.multi = importlib.import_module("procedural-universe_b200.multi") if self.world > 1 else None
         # an explicit stream: torch's default stream is the legacy stream (handle 0), for which nb_create would
@@ -275,7 +287,7 @@ class Ctx:
         self.torch.cuda.synchronize()
 
     def reduce(self, values, op="sum"):
-        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.cdev)
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return [float(x) for x in t.tolist()]
@@ -287,13 +299,14 @@ class Ctx:
         self.dist.all_gather_object(box, obj)
         return box
 
-    def new_sim(self, wl, world=None, rank=None):
+    def new_sim(self, wl, world=None, rank=None, splits=None):
         pkg = self.pkg
         world = self.world if world is None else world
         rank = self.rank if rank is None else rank
         mode = pkg.MODE_ALLPAIRS if wl["mode"] == "allpairs" else pkg.MODE_BARNESHUT
         return pkg.Sim(mode=mode, theta=wl.get("theta", 2.0), device=self.local_rank, rank=rank, world=world,
-                       stream=self.stream.cuda_stream, source_splits=self.args.splits, kernel_variant=self.args.variant)
+                       stream=self.stream.cuda_stream, source_splits=self.args.splits if splits is None else splits,
+                       kernel_variant=self.args.variant)
 
     def connect(self, sim):
         if self.world > 1:
@@ -316,6 +329,23 @@ def seed_workload(pkg, wl, out=None):
         return p
     out[:] = p
     return out
+
+
+T_START = time.perf_counter()
+
+
+def log(ctx, msg):
+    """Progress on stderr (every rank): a hung multi-process run must show where it stopped."""
+    print(f"[bench {time.perf_counter() - T_START:7.1f}s rank {ctx.rank}] {msg}", file=sys.stderr, flush=True)
+
+
+def guarded(fn, what):
+    """Rank-0-only extras (checker runs, probes) must not throw: an exception on one rank alone would leave the
+    other ranks inside the next collective."""
+    try:
+        return fn()
+    except Exception as exc:
+        return {"error": f"{what}: {type(exc).__name__}: {exc}"}
 
 
 def _rel(a, b):
@@ -384,16 +414,21 @@ def parity_check(ctx, sim, wl, particles, after_first_step=False, direct=None):
 
     tsel = sample_targets(n)
     got = fast(tsel)
-    if ctx.rank == 0:
-        if direct is None:
-            direct = sim.direct_accelerations(tsel)
-        out["device_direct"] = dict(_stats(_rel(got, direct)), what="fast path vs nb_direct_accel (restated reference law, fp64 sums) on the device")
-    if particles is not None and n <= (1 << 20) and ctx.rank == 0:
+    def device_direct():
+        d = direct if direct is not None else sim.direct_accelerations(tsel)
+        return dict(_stats(_rel(got, d)), what="fast path vs nb_direct_accel (restated reference law, fp64 sums) on the device")
+
+    def live_checker():
         from oracle import checker
         t16 = tsel[:: max(1, len(tsel) // 16)][:16]
         want = checker.allpairs_accel(particles, t16) if wl["mode"] == "allpairs" else checker.barneshut_accel(particles, wl.get("theta", 0.5), t16)
         idx = np.searchsorted(tsel, t16)
-        out["live_checker"] = dict(_stats(_rel(got[idx], want)), checker=checker.kind())
+        return dict(_stats(_rel(got[idx], want)), checker=checker.kind())
+
+    if ctx.rank == 0:
+        out["device_direct"] = guarded(device_direct, "nb_direct_accel")
+        if particles is not None and n <= (1 << 20):
+            out["live_checker"] = guarded(live_checker, "oracle")
     return out if ctx.rank == 0 else None
 
 
@@ -423,14 +458,21 @@ def run_workload(ctx, name, steps, warmup, headline):
         particles = seed_workload(pkg, wl)      # multi-GB scenes: pageable, the e2e leg is not run on them
     t_seed = time.perf_counter() - t_seed
 
+    log(ctx, f"{name}: seeded in {t_seed:.1f} s")
     sim = ctx.new_sim(wl)
     sim.init(particles)
     ctx.connect(sim)
     first, count = sim.owned_range()
+    log(ctx, f"{name}: initialised, peers connected")
 
     deferred = wl["mode"] == "allpairs" and n > (1 << 20)
     if deferred:
-        direct = sim.direct_accelerations(sample_targets(n)) if rank == 0 else None
+        direct = None
+        if rank == 0:
+            try:
+                direct = sim.direct_accelerations(sample_targets(n))
+            except Exception:
+                direct = None
     else:
         parity = parity_check(ctx, sim, wl, particles)
 
@@ -440,12 +482,19 @@ def run_workload(ctx, name, steps, warmup, headline):
         ke, pe, ns = ctx.reduce([ke, pe, float(ns)])
         return ke, pe, int(ns)
 
+    log(ctx, f"{name}: parity checked")
     energy = {"start": total_energy()} if "energy_stride" in wl else None
 
     def walk_counters():
         """One instrumented traversal (untimed) of this rank's targets, summed over the ranks."""
         mine = sim.walk_stats()
-        tw = ctx.reduce([mine["cell_evals"], mine["leaf_evals"], mine["visits"], float(sim.inbounds()) if rank == 0 else 0.0])
+        inside = 0.0
+        if rank == 0:
+            try:
+                inside = float(sim.inbounds())
+            except Exception:
+                inside = -1.0
+        tw = ctx.reduce([mine["cell_evals"], mine["leaf_evals"], mine["visits"], inside])
         return {"cell_evals": int(tw[0]), "leaf_evals": int(tw[1]), "visits": int(tw[2]), "bodies_inside_root_cube": int(tw[3]), "rank0": mine}
 
     # ---- device-resident steps: nothing between the events but the L2 flush and nb_step ----------
@@ -457,6 +506,7 @@ def run_workload(ctx, name, steps, warmup, headline):
     if not e2e_steps and n > (1 << 24):
         particles = None                        # multi-GB host image: the device holds the state from here on
     ctx.barrier()
+    log(ctx, f"{name}: {warmup} warm-up steps done")
     walk_start = walk_counters() if wl["mode"] == "bh" else None
     ctx.barrier()
     sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
@@ -472,6 +522,7 @@ def run_workload(ctx, name, steps, warmup, headline):
     ctx.barrier()
     clocks = sampler.stop() if sampler else None
     total_ms = ctx.reduce([e0.elapsed_time(e1)], "max")[0]
+    log(ctx, f"{name}: {steps} timed steps, {total_ms / steps:.3f} ms/step")
     # CUDA events recorded by the library on the launching stream around the dominant kernel and the tree build of
     # every step (a ring of 64), read only now
     kms, build_ms, timed_steps = sim.step_timing_mean(steps)
@@ -494,7 +545,13 @@ def run_workload(ctx, name, steps, warmup, headline):
         ctx.barrier()
         e2e_s = ctx.reduce([time.perf_counter() - t0], "max")[0]
 
-    fp32_peak = sim.probe_fp32_peak() if rank == 0 else None
+    log(ctx, f"{name}: counters, hashes, e2e done")
+    fp32_peak = None
+    if rank == 0:
+        try:
+            fp32_peak = sim.probe_fp32_peak()
+        except Exception:
+            fp32_peak = float("nan")
     sim.close()
     if rank != 0:
         return None
@@ -570,16 +627,20 @@ def run_bitwise(ctx, name, steps):
     flags), then the same steps on rank 0 alone; the state checksums must be equal."""
     wl = WORKLOADS[name]
     particles = seed_workload(ctx.pkg, wl)
-    sim = ctx.new_sim(wl)
+    # all-pairs: the number of source splits (0 = sized to fill the GPU for THIS rank's target count) decides the order
+    # in which a target's partial sums are added -- pinned, so that N ranks and one GPU add in the same order
+    splits = 8 if wl["mode"] == "allpairs" else None
+    sim = ctx.new_sim(wl, splits=splits)
     sim.init(particles)
     ctx.connect(sim)
     sim.step(wl["dt"], steps)
     multi = state_hashes(ctx, sim)
+    log(ctx, f"bitwise {name}: {steps} steps on {ctx.world} ranks hashed")
     ctx.barrier()
     sim.close()
     single = None
     if ctx.rank == 0:
-        one = ctx.new_sim(wl, world=1, rank=0)
+        one = ctx.new_sim(wl, world=1, rank=0, splits=splits)
         one.init(particles)
         one.step(wl["dt"], steps)
         single = one.state_hash()
@@ -594,7 +655,7 @@ def run_bitwise(ctx, name, steps):
 def secondary_plan(args, world):
     """(workload, steps, warmup) beside the headline: the other BASELINE.json configs that fit the GPUs at hand.
     Barnes-Hut runs get >= 200 steps so that the 100 ms clock sampler sees the timed region."""
-    if args.secondary == "none" or args.workload != "allpairs_1m":
+    if args.secondary == "none" or (args.secondary == "auto" and args.workload != "allpairs_1m"):
         return []
     if args.secondary != "auto":
         return [(w, max(args.steps, 200) if WORKLOADS[w]["mode"] == "bh" else args.steps, 3) for w in args.secondary.split(",") if w]

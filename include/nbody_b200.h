@@ -145,9 +145,21 @@ NB_API int nb_seed_host(int kind, void* particles, size_t n, size_t stride, uint
  * each other with `approach_speed` (velocity units). */
 NB_API int nb_seed_collision_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale,
                            float separation, double approach_speed);
-/* Device-side galaxy seeder: counter-based generator, same distributions as GalaxySeeder.cpp but
- * not the same random stream; initialises the handle directly (no host round trip). */
+/* The same three seeders ON THE DEVICE, producing bit for bit the records nb_seed_host (and the reference built
+ * with g++ / libstdc++) produces.  GalaxySeeder's single minstd_rand0 stream with data-dependent draw counts
+ * (polar-method rejection, cached normal variates, the disk's rejection loop, GalaxySeeder.cpp:43-143) is parsed in
+ * parallel: LCG jump-ahead, per-chunk transition tables over all entry offsets, a composed scan, then one thread per
+ * pair of bodies (csrc/seed_device.cu).  nb_seed_device copies the records to a HOST array (bytes the seeders do
+ * not write are zero); `device` is the CUDA device to use. */
+NB_API int nb_seed_device(int kind, int device, void* particles, size_t n, size_t stride, uint64_t seed, const nb_seed_options* opt);
+/* GalaxySeeder<Particle>(particles, scale).Seed(seed) straight into the handle -- no host round trip; every rank
+ * of a multi-GPU run seeds all bodies (it needs all positions) and keeps its own shard's velocities. */
 NB_API int nb_seed_galaxy_device(nb_handle h, size_t n, uint64_t seed, float scale);
+/* nb_seed_collision_host's scene straight into the handle. */
+NB_API int nb_seed_collision_device(nb_handle h, size_t n, uint64_t seed, float scale, float separation, double approach_speed);
+/* Records of the handle's device image of the Particle array (as seeded / last uploaded / last written back) for a
+ * list of body indices: records[k][104].  Lets a caller check a few bodies of a 7 GB scene without reading it back. */
+NB_API int nb_get_aos_records(nb_handle h, const uint32_t* bodies, size_t k, void* records);
 
 /* ---- INBodySim::Update --------------------------------------------------------------------- */
 /* nsteps x Update(dt) on device-resident state -- BruteForceCPU.cpp:45-74 / BarnesHut.cpp:44-96:

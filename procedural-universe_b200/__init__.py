@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     load,
     seed_galaxy_host,
     seed_host,
+    seed_device,
     SeedOptions,
     LWPARTICLE_DTYPE,
     SEEDER_RANDOM,

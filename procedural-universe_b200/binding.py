@@ -94,6 +94,9 @@ def load():
     L.nb_seed_host.argtypes = [C.c_int, vp, sz, sz, C.c_uint64, C.POINTER(SeedOptions)]
     L.nb_seed_collision_host.argtypes = [vp, sz, sz, C.c_uint64, f32, f32, f64]
     L.nb_seed_galaxy_device.argtypes = [vp, sz, C.c_uint64, f32]
+    L.nb_seed_collision_device.argtypes = [vp, sz, C.c_uint64, f32, f32, f64]
+    L.nb_seed_device.argtypes = [C.c_int, C.c_int, vp, sz, sz, C.c_uint64, vp]
+    L.nb_get_aos_records.argtypes = [vp, vp, sz, vp]
     L.nb_step.argtypes = [vp, f32, C.c_int]
     L.nb_update_aos.argtypes = [vp, vp, sz, sz, f32]
     L.nb_sync.argtypes = [vp]
@@ -160,6 +163,21 @@ def seed_host(kind, n, seed=0, scale=1.0, colours=None, lw=False):
     if colours is not None:
         (o.red[0], o.red[1]), (o.green[0], o.green[1]), (o.blue[0], o.blue[1]) = colours
     _check(load().nb_seed_host(kind, p.ctypes.data, n, dtype.itemsize, seed, C.byref(o)))
+    return p
+
+
+def seed_device(kind, n, seed=0, scale=1.0, colours=None, lw=False, device=0):
+    """The same seeders run ON THE DEVICE (csrc/seed_device.cu: parallel parse of the minstd_rand0 stream), bit for
+    bit equal to seed_host / the reference; records are copied back to a host array."""
+    dtype = LWPARTICLE_DTYPE if lw else PARTICLE_DTYPE
+    p = np.zeros(n, dtype=dtype)
+    o = SeedOptions()
+    _check(load().nb_seed_default_options(C.byref(o)))
+    o.layout = LAYOUT_LWPARTICLE if lw else LAYOUT_PARTICLE
+    o.scale = scale
+    if colours is not None:
+        (o.red[0], o.red[1]), (o.green[0], o.green[1]), (o.blue[0], o.blue[1]) = colours
+    _check(load().nb_seed_device(kind, device, p.ctypes.data, n, dtype.itemsize, seed, C.byref(o)))
     return p
 
 
@@ -248,6 +266,17 @@ class Sim:
     def seed_galaxy_device(self, n, seed=42, scale=1.0):
         _check(self._L.nb_seed_galaxy_device(self._h, n, seed, scale))
         self.n = n
+
+    def seed_collision_device(self, n, seed=42, scale=1.0, separation=2000.0, approach_speed=2e16):
+        _check(self._L.nb_seed_collision_device(self._h, n, seed, scale, separation, approach_speed))
+        self.n = n
+
+    def aos_records(self, bodies):
+        """Records of the device image of the Particle array for the listed bodies."""
+        b = np.ascontiguousarray(bodies, dtype=np.uint32)
+        out = np.zeros(len(b), dtype=PARTICLE_DTYPE)
+        _check(self._L.nb_get_aos_records(self._h, b.ctypes.data, len(b), out.ctypes.data))
+        return out
 
     # --- INBodySim::Update
     def step(self, dt, nsteps=1):

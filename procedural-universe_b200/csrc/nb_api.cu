@@ -47,7 +47,7 @@ int preload_allpairs(nb_sim* h)
     return NB_OK;
 }
 
-static int reserve_aos(nb_sim* h, size_t bytes)
+int reserve_aos(nb_sim* h, size_t bytes)
 {
     if (h->d_aos_bytes >= bytes) return NB_OK;
     cudaFree(h->d_aos);
@@ -696,6 +696,32 @@ int nb_seed_galaxy_device(nb_handle h, size_t n, uint64_t seed, float scale)
     NB_CUDA(cudaSetDevice(h->cfg.device));
     NB_CHECK(set_bodies(h, n));
     return nb::seed_galaxy_device(h, n, seed, scale);
+}
+
+int nb_seed_collision_device(nb_handle h, size_t n, uint64_t seed, float scale, float separation, double approach_speed)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(n >= 2, NB_ERR_ARG, "the collision scene needs at least two bodies");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CHECK(set_bodies(h, n));
+    return nb::seed_collision_device(h, n, seed, scale, separation, approach_speed);
+}
+
+int nb_get_aos_records(nb_handle h, const uint32_t* bodies, size_t k, void* records)
+{
+    NB_REQUIRE(h != nullptr && bodies != nullptr && records != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->n > 0 && h->d_aos != nullptr && h->d_aos_bytes >= h->n * NB_PARTICLE_STRIDE, NB_ERR_STATE,
+               "no device image of the Particle array (nb_init_aos / nb_seed_*_device / nb_update_aos create it)");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < k; ++i)
+    {
+        NB_REQUIRE(bodies[i] < h->n, NB_ERR_ARG, "body index out of range");
+        NB_CUDA(cudaMemcpy(static_cast<unsigned char*>(records) + i * NB_PARTICLE_STRIDE,
+                           static_cast<const unsigned char*>(h->d_aos) + (size_t)bodies[i] * NB_PARTICLE_STRIDE, NB_PARTICLE_STRIDE,
+                           cudaMemcpyDeviceToHost));
+    }
+    return NB_OK;
 }
 
 }  // extern "C"

@@ -190,6 +190,8 @@ void p2p_release(nb_sim* h);
 // seed_host.cpp / seed_device.cu
 int seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, float scale);
 int seed_galaxy_device(nb_sim* h, size_t n, uint64_t seed, float scale);
+int seed_collision_device(nb_sim* h, size_t n, uint64_t seed, float scale, float separation, double approach_speed);
+int reserve_aos(nb_sim* h, size_t bytes);
 
 // energy.cu
 int energy(nb_sim* h, double* ke, double* pe);

@@ -118,4 +118,4 @@ def test_two_process_peer_memory_path_is_bitwise_equal_to_one_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-    assert line["multi_gpu_bitwise"] is True, line
+    assert line["multi_gpu_bitwise"] is True, json.dumps(line)
