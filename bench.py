@@ -387,10 +387,9 @@ def parity_check(ctx, sim, wl, particles, after_first_step=False, direct=None):
         g = np.load(gold_path)
         targets = g["targets"]
         rec = np.ascontiguousarray(g["records"]).view(ctx.pkg.PARTICLE_DTYPE).reshape(-1)
-        same = None
-        if particles is not None:
-            mine = particles[targets]
-            same = bool(all(np.array_equal(mine[f], rec[f]) for f in ("Position", "Velocity", "Mass")))
+        # the bodies themselves: the host array, or -- seeded on the device -- the device image of the sampled records
+        mine = particles[targets] if particles is not None else (sim.aos_records(targets) if not after_first_step else None)
+        same = None if mine is None else bool(all(np.array_equal(mine[f], rec[f]) for f in ("Position", "Velocity", "Mass", "Colour")))
         got = fast(targets)
         mass = rec["Mass"][:, None]
         entry = {"file": "tests/golden/" + gold_file, "same_bodies_as_reference_seeder": same}
@@ -448,19 +447,30 @@ def run_workload(ctx, name, steps, warmup, headline):
     wl = WORKLOADS[name]
     n, dt = wl["n"], wl["dt"]
     e2e_steps = 0 if args.no_e2e or n * 104 > (2 << 30) else (steps if headline else min(steps, 5))
+    if not headline and wl["mode"] == "allpairs" and n > (1 << 20):
+        e2e_steps = 0                           # a 2^24-body all-pairs Update is 14 s on 8 GPUs: the device-resident steps are all that is run
 
     # pinned host AoS array: the caller's std::vector<Particle>
     t_seed = time.perf_counter()
     if e2e_steps:
         host = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
         particles = seed_workload(pkg, wl, host.numpy().view(pkg.PARTICLE_DTYPE))
-    else:
+        seeded_on = "host (nb_seed_host, pinned array)"
+    elif "mass_scale" in wl:
         particles = seed_workload(pkg, wl)      # multi-GB scenes: pageable, the e2e leg is not run on them
-    t_seed = time.perf_counter() - t_seed
-
-    log(ctx, f"{name}: seeded in {t_seed:.1f} s")
+        seeded_on = "host (nb_seed_host)"
+    else:
+        particles = None                        # multi-GB scenes without an e2e leg: seeded on the device, below
+        seeded_on = "device (nb_seed_*_device: parallel parse of the reference's random stream, bit-exact)"
     sim = ctx.new_sim(wl)
-    sim.init(particles)
+    if particles is not None:
+        sim.init(particles)
+    elif wl.get("scene") == "collision":
+        sim.seed_collision_device(n, wl["seed"], 1.0, **COLLISION)
+    else:
+        sim.seed_galaxy_device(n, wl["seed"], 1.0)
+    t_seed = time.perf_counter() - t_seed
+    log(ctx, f"{name}: seeded on the {seeded_on.split()[0]} and initialised in {t_seed:.1f} s")
     ctx.connect(sim)
     first, count = sim.owned_range()
     log(ctx, f"{name}: initialised, peers connected")
@@ -531,12 +541,18 @@ def run_workload(ctx, name, steps, warmup, headline):
     if energy is not None:
         energy["end"] = total_energy()
     hashes = state_hashes(ctx, sim) if world > 1 else None
+    log(ctx, f"{name}: state hashed")
 
     walk = walk_counters() if wl["mode"] == "bh" else None       # the state the last timed steps ran on
 
+    log(ctx, f"{name}: walk counted")
     # ---- end to end through the host-array contract ------------------------------------------
     e2e_s = None
     if e2e_steps:
+        # the caller's array must hold the CURRENT state (the adapter's array always does: every Update writes it
+        # back): a shard handle re-reads only its own records, and the tree code needs every rank to see the same bodies
+        sim.read(particles)
+        ctx.barrier()
         sim.update(particles, dt)           # warm-up of the AoS path
         ctx.barrier()
         t0 = time.perf_counter()
@@ -570,7 +586,7 @@ def run_workload(ctx, name, steps, warmup, headline):
         "config": {"workload": wl["desc"], "name": name, "bodies": n, "dt": dt,
                    "parallelism": f"target-sharded x{world}" + (f", exchange={args.exchange}" if world > 1 else ""),
                    "l2": "256 MiB memset between timed steps (inside the timed region); sources (16 B/body) are re-read from L2 by design",
-                   "kernel_variant": args.variant, "host_seeding_s": t_seed},
+                   "kernel_variant": args.variant, "seeded_on": seeded_on, "seed_and_init_s": t_seed},
         "gpu_launches": launches,
     }
     pk = peaks()
@@ -707,6 +723,7 @@ def main():
             r = run_workload(ctx, name, steps, warmup, headline=False)
         except Exception as exc:            # a secondary workload must not take the headline down with it
             r = {"error": f"{type(exc).__name__}: {exc}"}
+            log(ctx, f"{name}: FAILED {r['error']}")
         if ctx.rank == 0:
             secondary[name] = r
     if ctx.world > 1 and args.secondary != "none" and args.exchange == "p2p":
