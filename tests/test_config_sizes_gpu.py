@@ -119,3 +119,46 @@ def test_two_process_peer_memory_path_is_bitwise_equal_to_one_gpu():
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["multi_gpu_bitwise"] is True, json.dumps(line)
+
+
+def test_collision_1m_energy_and_trajectories_track_the_reference(pkg):
+    """The two-galaxy scene of configs[4] at 2^20 bodies, 100 steps, against the REFERENCE's Barnes-Hut CPU path
+    (tests/golden/make_golden_collision1m.py: ~35 minutes of oracle/_ref on 4 pool workers).
+
+    At this size the scene is already violent -- the reference's own energy drifts 4.7 % in 100 steps and its
+    kinetic energy grows 50-fold (dt = 0.02/60 under-resolves bodies of these masses once N is large) -- which is
+    exactly why the comparison is with the reference and not with zero: the GPU path has to drift the SAME way."""
+    g = load_golden("collision_n1048576_100steps.npz")
+    n, every, stride = int(g["n"]), int(g["every"]), int(g["stride"])
+    p = pkg.seed_collision_host(n, 42, 1.0, separation=float(g["separation"]), approach_speed=float(g["approach"]))
+    assert hashlib.sha256(p.view(np.uint8)).hexdigest() == str(g["sha256"])
+    sim = pkg.Sim(mode=pkg.MODE_BARNESHUT, theta=float(g["theta"]))
+    sim.init(p)
+    energies = []
+    for k in range(len(g["drift"])):
+        if k:
+            sim.step(float(g["dt"]), every)
+        ke, pe, ns = sim.energy_sampled(stride)
+        energies.append((ke, pe))
+    e = np.array(energies)
+    # the estimator itself (oracle/port.py energy_sampled restates nb_energy_sampled): same numbers at step 0
+    assert abs(e[0, 0] - g["energies"][0, 0]) < 1e-12 * abs(e[0, 0]) and abs(e[0, 1] - g["energies"][0, 1]) < 1e-6 * abs(e[0, 1])
+    tot = e.sum(axis=1)
+    drift = np.abs(tot - tot[0]) / abs(tot[0])
+    print("energy drift ours      (N=2^20, every 25 steps):", drift)
+    print("energy drift reference (N=2^20, every 25 steps):", g["drift"])
+    # north star: within 2x the reference's; in fact it follows it checkpoint by checkpoint
+    assert np.all(drift[1:] <= 2.0 * g["drift"][1:])
+    assert np.all(np.abs(drift[1:] - g["drift"][1:]) <= 0.1 * g["drift"][1:])
+    # kinetic and potential energy separately, at every checkpoint
+    assert np.all(np.abs(e - g["energies"]) <= 2e-2 * np.abs(g["energies"]))
+    # trajectories of every 256th body after 100 steps: the median body is where the reference put it
+    q = np.zeros(n, dtype=pkg.PARTICLE_DTYPE)
+    sim.read(q)
+    moved = np.linalg.norm(g["final_pos_sample"] - p["Position"][::stride], axis=1)
+    off = np.linalg.norm(q["Position"][::stride] - g["final_pos_sample"], axis=1)
+    print("position error / displacement after 100 steps: median %.2e, 90%% %.2e" % (np.median(off / moved), np.quantile(off / moved, 0.9)))
+    assert np.median(off / moved) < 1e-3
+    vrel = np.linalg.norm(q["Velocity"][::stride] - g["final_vel_sample"], axis=1) / np.linalg.norm(g["final_vel_sample"], axis=1)
+    assert np.median(vrel) < 1e-3
+    sim.close()
