@@ -445,7 +445,7 @@ def run_workload(ctx, name, steps, warmup, headline):
     torch, pkg, args = ctx.torch, ctx.pkg, ctx.args
     rank, world = ctx.rank, ctx.world
     wl = WORKLOADS[name]
-    n, dt = wl["n"], wl["dt"]
+    n, dt = wl["n"], wl["dt"] * args.dt_scale
     e2e_steps = 0 if args.no_e2e or n * 104 > (2 << 30) else (steps if headline else min(steps, 5))
     if not headline and wl["mode"] == "allpairs" and n > (1 << 20):
         e2e_steps = 0                           # a 2^24-body all-pairs Update is 14 s on 8 GPUs: the device-resident steps are all that is run
@@ -456,9 +456,6 @@ def run_workload(ctx, name, steps, warmup, headline):
         host = torch.empty(n * 104, dtype=torch.uint8).pin_memory()
         particles = seed_workload(pkg, wl, host.numpy().view(pkg.PARTICLE_DTYPE))
         seeded_on = "host (nb_seed_host, pinned array)"
-    elif "mass_scale" in wl:
-        particles = seed_workload(pkg, wl)      # multi-GB scenes: pageable, the e2e leg is not run on them
-        seeded_on = "host (nb_seed_host)"
     else:
         particles = None                        # multi-GB scenes without an e2e leg: seeded on the device, below
         seeded_on = "device (nb_seed_*_device: parallel parse of the reference's random stream, bit-exact)"
@@ -469,6 +466,8 @@ def run_workload(ctx, name, steps, warmup, headline):
         sim.seed_collision_device(n, wl["seed"], 1.0, **COLLISION)
     else:
         sim.seed_galaxy_device(n, wl["seed"], 1.0)
+    if particles is None and "mass_scale" in wl:
+        sim.scale_masses(wl["mass_scale"])
     t_seed = time.perf_counter() - t_seed
     log(ctx, f"{name}: seeded on the {seeded_on.split()[0]} and initialised in {t_seed:.1f} s")
     ctx.connect(sim)
@@ -631,10 +630,21 @@ def run_workload(ctx, name, steps, warmup, headline):
     if energy is not None:
         (k0, p0, ns), (k1, p1, _) = energy["start"], energy["end"]
         res["energy"] = {
-            "steps": warmup + steps, "kinetic": [k0, k1], "potential": [p0, p1],
+            "steps": warmup + steps, "dt": dt, "physical_time": (warmup + steps) * dt, "kinetic": [k0, k1], "potential": [p0, p1],
             "drift": abs((k1 + p1) - (k0 + p0)) / abs(k0 + p0),
             "estimator": f"E = sum 1/2 m v^2 (exact) + 2.3e13 * sum U(r) estimated from {ns} bodies (every {wl['energy_stride']}th) x all sources, same bodies at both times",
         }
+    if energy is not None and "mass_scale" in wl:
+        # the scene with the total mass of the 4096-body golden: the reference's own Barnes-Hut path drifts by this much
+        # over the same number of steps at the same dt (tests/golden/energy_drift_n4096.npz, checkpoints every 100 steps)
+        try:
+            g = np.load(os.path.join(ROOT, "tests", "golden", "energy_drift_n4096.npz"))
+            k = min(len(g["drift"]) - 1, max(1, int(round((warmup + steps) / 100.0))))
+            ref_drift = float(g["drift"][k])
+            res["energy"]["reference_drift"] = {"n": 4096, "steps": 100 * k, "drift": ref_drift, "source": "tests/golden/energy_drift_n4096.npz (reference BarnesHut::Update)"}
+            res["energy"]["ratio_vs_reference"] = res["energy"]["drift"] / ref_drift
+        except Exception:
+            pass
     return res
 
 
@@ -698,6 +708,7 @@ def main():
                     help="N > 1: fused kick-drift + peer-memory stores (p2p) or kick-drift + ncclAllGather (nccl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dt-scale", type=float, default=1.0, help="multiplies the workload's dt (energy convergence runs: same physical time with --steps scaled up)")
     ap.add_argument("--bitwise-only", action="store_true", help="N > 1: only compare the multi-process path with a one-GPU rerun")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -157,6 +157,9 @@ NB_API int nb_seed_device(int kind, int device, void* particles, size_t n, size_
 NB_API int nb_seed_galaxy_device(nb_handle h, size_t n, uint64_t seed, float scale);
 /* nb_seed_collision_host's scene straight into the handle. */
 NB_API int nb_seed_collision_device(nb_handle h, size_t n, uint64_t seed, float scale, float separation, double approach_speed);
+/* Multiplies every body's Mass by `factor` in the device image and re-derives the device state from it (a scene
+ * variant: the same bodies with the total mass of a smaller scene).  Needs the image (nb_init_aos / nb_seed_*_device). */
+NB_API int nb_scale_masses(nb_handle h, double factor);
 /* Records of the handle's device image of the Particle array (as seeded / last uploaded / last written back) for a
  * list of body indices: records[k][104].  Lets a caller check a few bodies of a 7 GB scene without reading it back. */
 NB_API int nb_get_aos_records(nb_handle h, const uint32_t* bodies, size_t k, void* records);

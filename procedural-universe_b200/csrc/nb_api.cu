@@ -316,6 +316,7 @@ int nb_init_aos(nb_handle h, const void* particles, size_t n, size_t stride)
     NB_CHECK(set_bodies(h, n));
     NB_CHECK(reserve_aos(h, n * stride));
     NB_CUDA(cudaMemcpyAsync(h->d_aos, particles, n * stride, cudaMemcpyHostToDevice, h->stream));
+    h->d_aos_stride = stride;
     h->last_launches = 0;
     NB_CHECK(launch_unpack_aos(h, stride, 0, n));
     NB_CUDA(cudaStreamSynchronize(h->stream));
@@ -346,7 +347,7 @@ int nb_init_soa(nb_handle h, const float* pos3, const double* vel3, const double
         cudaError_t e = cudaMemcpyAsync(h->d_aos, tmp, n * stride, cudaMemcpyHostToDevice, h->stream);
         if (e != cudaSuccess) { nb::set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); rc = NB_ERR_CUDA; }
     }
-    if (rc == NB_OK) { h->last_launches = 0; rc = launch_unpack_aos(h, stride, 0, n); }
+    if (rc == NB_OK) { h->d_aos_stride = stride; h->last_launches = 0; rc = launch_unpack_aos(h, stride, 0, n); }
     cudaStreamSynchronize(h->stream);
     cudaFreeHost(tmp);
     return rc;
@@ -404,6 +405,7 @@ int nb_update_aos(nb_handle h, void* particles, size_t n, size_t stride, float d
     const bool fresh = (n != h->n);
     if (fresh) NB_CHECK(set_bodies(h, n));
     NB_CHECK(reserve_aos(h, n * stride));
+    h->d_aos_stride = stride;
     const bool whole = fresh || h->cfg.world == 1;
     const size_t begin = whole ? 0 : h->first, end = whole ? n : h->first + h->count;
     NB_REQUIRE(whole || h->exchanged, NB_ERR_STATE, "positions of remote ranks are stale");
@@ -707,10 +709,25 @@ int nb_seed_collision_device(nb_handle h, size_t n, uint64_t seed, float scale, 
     return nb::seed_collision_device(h, n, seed, scale, separation, approach_speed);
 }
 
+int nb_scale_masses(nb_handle h, double factor)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    NB_REQUIRE(h->n > 0 && h->d_aos != nullptr && h->d_aos_stride >= NB_PARTICLE_STRIDE, NB_ERR_STATE,
+               "no device image of the Particle array (nb_init_aos / nb_seed_*_device create it)");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CHECK(nb::launch_scale_masses(h, factor));
+    h->last_launches = 0;
+    NB_CHECK(launch_unpack_aos(h, h->d_aos_stride, 0, h->n));
+    h->acc_valid = false;
+    h->tree.built = false;
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    return NB_OK;
+}
+
 int nb_get_aos_records(nb_handle h, const uint32_t* bodies, size_t k, void* records)
 {
     NB_REQUIRE(h != nullptr && bodies != nullptr && records != nullptr, NB_ERR_ARG, "null argument");
-    NB_REQUIRE(h->n > 0 && h->d_aos != nullptr && h->d_aos_bytes >= h->n * NB_PARTICLE_STRIDE, NB_ERR_STATE,
+    NB_REQUIRE(h->n > 0 && h->d_aos != nullptr && h->d_aos_stride >= NB_PARTICLE_STRIDE, NB_ERR_STATE,
                "no device image of the Particle array (nb_init_aos / nb_seed_*_device / nb_update_aos create it)");
     NB_CUDA(cudaSetDevice(h->cfg.device));
     NB_CUDA(cudaStreamSynchronize(h->stream));
@@ -718,7 +735,7 @@ int nb_get_aos_records(nb_handle h, const uint32_t* bodies, size_t k, void* reco
     {
         NB_REQUIRE(bodies[i] < h->n, NB_ERR_ARG, "body index out of range");
         NB_CUDA(cudaMemcpy(static_cast<unsigned char*>(records) + i * NB_PARTICLE_STRIDE,
-                           static_cast<const unsigned char*>(h->d_aos) + (size_t)bodies[i] * NB_PARTICLE_STRIDE, NB_PARTICLE_STRIDE,
+                           static_cast<const unsigned char*>(h->d_aos) + (size_t)bodies[i] * h->d_aos_stride, NB_PARTICLE_STRIDE,
                            cudaMemcpyDeviceToHost));
     }
     return NB_OK;

@@ -112,6 +112,7 @@ struct nb_sim
     float* wmax = nullptr;       // [1] max_j G*m_j over all sources (bit pattern, kept by atomicMax)
     void* d_aos = nullptr;       // device image of the caller's AoS array
     size_t d_aos_bytes = 0;
+    size_t d_aos_stride = 0;     // record stride of the image (0: no image yet)
 
     int ap_kernel = 0;           // index into allpairs_table()
     int ap_splits = 1;
@@ -192,6 +193,7 @@ int seed_galaxy_host(void* particles, size_t n, size_t stride, uint64_t seed, fl
 int seed_galaxy_device(nb_sim* h, size_t n, uint64_t seed, float scale);
 int seed_collision_device(nb_sim* h, size_t n, uint64_t seed, float scale, float separation, double approach_speed);
 int reserve_aos(nb_sim* h, size_t bytes);
+int launch_scale_masses(nb_sim* h, double factor);
 
 // energy.cu
 int energy(nb_sim* h, double* ke, double* pe);

@@ -829,6 +829,7 @@ int seed_galaxy_device(nb_sim* h, size_t n, uint64_t seed, float scale)
     NB_CHECK(reserve_aos(h, n * stride));
     NB_CUDA(cudaMemsetAsync(h->d_aos, 0, n * stride, h->stream));
     NB_CHECK(seed_records_device(h->stream, NB_SEEDER_GALAXY, static_cast<unsigned char*>(h->d_aos), n, stride, seed, o));
+    h->d_aos_stride = stride;
     h->last_launches = 0;
     NB_CHECK(launch_unpack_aos(h, stride, 0, n));
     NB_CUDA(cudaStreamSynchronize(h->stream));
@@ -849,9 +850,25 @@ int seed_collision_device(nb_sim* h, size_t n, uint64_t seed, float scale, float
     NB_CHECK(seed_records_device(h->stream, NB_SEEDER_GALAXY, aos + half * stride, n - half, stride, seed + 1, o));
     k_seed_collide<<<(unsigned int)((n + 255) / 256), 256, 0, h->stream>>>(aos, n, half, stride, separation, approach_speed);
     NB_CUDA(cudaGetLastError());
+    h->d_aos_stride = stride;
     h->last_launches = 0;
     NB_CHECK(launch_unpack_aos(h, stride, 0, n));
     NB_CUDA(cudaStreamSynchronize(h->stream));
+    return NB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_scale_masses(unsigned char* __restrict__ aos, unsigned long long n, unsigned long long stride, double factor)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* m = reinterpret_cast<double*>(aos + i * stride + NB_OFF_MASS);
+    *m = __dmul_rn(*m, factor);
+}
+
+int launch_scale_masses(nb_sim* h, double factor)
+{
+    k_scale_masses<<<(unsigned int)((h->n + 255) / 256), 256, 0, h->stream>>>(static_cast<unsigned char*>(h->d_aos), h->n, h->d_aos_stride, factor);
+    NB_CUDA(cudaGetLastError());
     return NB_OK;
 }
 
