@@ -445,6 +445,8 @@ def run_workload(ctx, name, steps, warmup, headline):
     torch, pkg, args = ctx.torch, ctx.pkg, ctx.args
     rank, world = ctx.rank, ctx.world
     wl = WORKLOADS[name]
+    if args.energy_stride > 0 and "energy_stride" in wl:
+        wl = dict(wl, energy_stride=args.energy_stride)
     n, dt = wl["n"], wl["dt"] * args.dt_scale
     e2e_steps = 0 if args.no_e2e or n * 104 > (2 << 30) else (steps if headline else min(steps, 5))
     if not headline and wl["mode"] == "allpairs" and n > (1 << 20):
@@ -708,6 +710,7 @@ def main():
                     help="N > 1: fused kick-drift + peer-memory stores (p2p) or kick-drift + ncclAllGather (nccl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--energy-stride", type=int, default=0, help="energy estimator: every k-th body x all sources (0 = the workload's default)")
     ap.add_argument("--dt-scale", type=float, default=1.0, help="multiplies the workload's dt (energy convergence runs: same physical time with --steps scaled up)")
     ap.add_argument("--bitwise-only", action="store_true", help="N > 1: only compare the multi-process path with a one-GPU rerun")
     args = ap.parse_args()
