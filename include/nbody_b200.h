@@ -157,6 +157,10 @@ NB_API int nb_seed_device(int kind, int device, void* particles, size_t n, size_
 NB_API int nb_seed_galaxy_device(nb_handle h, size_t n, uint64_t seed, float scale);
 /* nb_seed_collision_host's scene straight into the handle. */
 NB_API int nb_seed_collision_device(nb_handle h, size_t n, uint64_t seed, float scale, float separation, double approach_speed);
+/* One-GPU Barnes-Hut steps of up to 2^21 bodies replay their ~40 launches as two CUDA graphs (tree build, walk),
+ * captured at the first step after Init / a theta change: same kernels, same arguments, same results.  On by
+ * default (environment NB_GRAPHS=0 disables it process-wide); this switches it per handle. */
+NB_API int nb_enable_graphs(nb_handle h, int on);
 /* Multiplies every body's Mass by `factor` in the device image and re-derives the device state from it (a scene
  * variant: the same bodies with the total mass of a smaller scene).  Needs the image (nb_init_aos / nb_seed_*_device). */
 NB_API int nb_scale_masses(nb_handle h, double factor);

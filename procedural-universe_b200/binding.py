@@ -98,6 +98,7 @@ def load():
     L.nb_seed_device.argtypes = [C.c_int, C.c_int, vp, sz, sz, C.c_uint64, vp]
     L.nb_get_aos_records.argtypes = [vp, vp, sz, vp]
     L.nb_scale_masses.argtypes = [vp, f64]
+    L.nb_enable_graphs.argtypes = [vp, C.c_int]
     L.nb_step.argtypes = [vp, f32, C.c_int]
     L.nb_update_aos.argtypes = [vp, vp, sz, sz, f32]
     L.nb_sync.argtypes = [vp]
@@ -271,6 +272,9 @@ class Sim:
     def seed_collision_device(self, n, seed=42, scale=1.0, separation=2000.0, approach_speed=2e16):
         _check(self._L.nb_seed_collision_device(self._h, n, seed, scale, separation, approach_speed))
         self.n = n
+
+    def enable_graphs(self, on):
+        _check(self._L.nb_enable_graphs(self._h, 1 if on else 0))
 
     def scale_masses(self, factor):
         _check(self._L.nb_scale_masses(self._h, factor))

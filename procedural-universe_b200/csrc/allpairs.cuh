@@ -526,7 +526,11 @@ k_allpairs_fold(const float4* __restrict__ posw, int n, int tgt_first, int tgt_c
 // instead of 6 T registers, which lets a thread own more targets (fewer LDS per interaction)
 // inside the 128-register budget, and b = S a of two source pairs shares one LDS.128.
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int T, int MINB, int UNROLL>
+// MIX selects, per group of operations, packed f32x2 (bit clear) or two scalar instructions (bit set):
+// bit 0 the three subtractions, bit 1 the d^2 chain, bit 2 t / u / x, bit 3 the three accumulations.  Measured
+// on B200 (tools/issue_probe.cu): an FFMA2 costs ~2.2 issue cycles, two scalar FFMA 2.0 -- packed math saves
+// issue slots, not pipe time, so the best mix depends on what else competes for the issue port.
+template <int THREADS, int T, int MINB, int UNROLL, int MIX = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_allpairs_fold2(const float4* __restrict__ posw, int n, int tgt_first, int tgt_count, int src_chunk,
                  double* __restrict__ out, float sc, float soft, const float* __restrict__ wmax)
@@ -608,19 +612,56 @@ k_allpairs_fold2(const float4* __restrict__ posw, int n, int tgt_first, int tgt_
 #pragma unroll
                 for (int t = 0; t < T; ++t)
                 {
-                    const float2 dx = __fadd2_rn(sx, npx[t]);
-                    const float2 dy = __fadd2_rn(sy, npy[t]);
-                    const float2 dz = __fadd2_rn(sz, npz[t]);
-                    float2 d2 = __fmul2_rn(dx, dx);
-                    d2 = __ffma2_rn(dy, dy, d2);
-                    d2 = __ffma2_rn(dz, dz, d2);
-                    const float2 tt = __ffma2_rn(d2, sa, sb);
-                    const float2 u = __fmul2_rn(d2, tt);
-                    const float2 x = __ffma2_rn(u, tt, eps2);
+                    float2 dx, dy, dz, d2, tt, u, x;
+                    if (MIX & 1)
+                    {
+                        dx = make_float2(sx.x + npx[t].x, sx.y + npx[t].y);
+                        dy = make_float2(sy.x + npy[t].x, sy.y + npy[t].y);
+                        dz = make_float2(sz.x + npz[t].x, sz.y + npz[t].y);
+                    }
+                    else
+                    {
+                        dx = __fadd2_rn(sx, npx[t]);
+                        dy = __fadd2_rn(sy, npy[t]);
+                        dz = __fadd2_rn(sz, npz[t]);
+                    }
+                    if (MIX & 2)
+                    {
+                        d2 = make_float2(dx.x * dx.x, dx.y * dx.y);
+                        d2 = make_float2(fmaf(dy.x, dy.x, d2.x), fmaf(dy.y, dy.y, d2.y));
+                        d2 = make_float2(fmaf(dz.x, dz.x, d2.x), fmaf(dz.y, dz.y, d2.y));
+                    }
+                    else
+                    {
+                        d2 = __fmul2_rn(dx, dx);
+                        d2 = __ffma2_rn(dy, dy, d2);
+                        d2 = __ffma2_rn(dz, dz, d2);
+                    }
+                    if (MIX & 4)
+                    {
+                        tt = make_float2(fmaf(d2.x, sa.x, sb.x), fmaf(d2.y, sa.y, sb.y));
+                        u = make_float2(d2.x * tt.x, d2.y * tt.y);
+                        x = make_float2(fmaf(u.x, tt.x, kEps), fmaf(u.y, tt.y, kEps));
+                    }
+                    else
+                    {
+                        tt = __ffma2_rn(d2, sa, sb);
+                        u = __fmul2_rn(d2, tt);
+                        x = __ffma2_rn(u, tt, eps2);
+                    }
                     const float2 s = make_float2(rsqrt_approx(x.x), rsqrt_approx(x.y));
-                    ax[t] = __ffma2_rn(s, dx, ax[t]);
-                    ay[t] = __ffma2_rn(s, dy, ay[t]);
-                    az[t] = __ffma2_rn(s, dz, az[t]);
+                    if (MIX & 8)
+                    {
+                        ax[t] = make_float2(fmaf(s.x, dx.x, ax[t].x), fmaf(s.y, dx.y, ax[t].y));
+                        ay[t] = make_float2(fmaf(s.x, dy.x, ay[t].x), fmaf(s.y, dy.y, ay[t].y));
+                        az[t] = make_float2(fmaf(s.x, dz.x, az[t].x), fmaf(s.y, dz.y, az[t].y));
+                    }
+                    else
+                    {
+                        ax[t] = __ffma2_rn(s, dx, ax[t]);
+                        ay[t] = __ffma2_rn(s, dy, ay[t]);
+                        az[t] = __ffma2_rn(s, dz, az[t]);
+                    }
                 }
             }
         }
@@ -668,6 +709,8 @@ struct AllPairsKernel
     { #KERNEL "<" #TH "," #T "," #MB ">", VAR, TH, T, MB, 0, KERNEL<TH, T, MB> }
 #define NB_AP_ENTRY4(TH, T, MB, UN) \
     { "k_allpairs_fold2<" #TH "," #T "," #MB "," #UN ">", 3, TH, T, MB, 5 * TH * 16 + 3 * T * TH * 8, k_allpairs_fold2<TH, T, MB, UN> }
+#define NB_AP_ENTRY5(TH, T, MB, UN, MIX) \
+    { "k_allpairs_fold2<" #TH "," #T "," #MB "," #UN ",mix" #MIX ">", 3, TH, T, MB, 5 * TH * 16 + 3 * T * TH * 8, k_allpairs_fold2<TH, T, MB, UN, MIX> }
 
 inline const AllPairsKernel* allpairs_table(int* count)
 {
@@ -710,6 +753,8 @@ inline const AllPairsKernel* allpairs_table(int* count)
         NB_AP_ENTRY4(256, 2, 3, 2),
         NB_AP_ENTRY4(384, 4, 1, 1),                      // 35
         NB_AP_ENTRY4(128, 6, 3, 1),
+        NB_AP_ENTRY5(256, 4, 2, 2, 8),                   // 37: scalar accumulations (50.2 TFLOP/s against 51.0 packed)
+        NB_AP_ENTRY5(256, 4, 2, 2, 15),                  // 38: all scalar (45.9): every mix of scalar and packed groups is slower than all packed
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <new>
 
+#include <cstdlib>
+
 #include "nb_internal.h"
 #include "allpairs.cuh"
 
@@ -20,8 +22,17 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+static void graphs_release(nb_sim* h)
+{
+    if (h->graph_build) cudaGraphExecDestroy(h->graph_build);
+    if (h->graph_walk) cudaGraphExecDestroy(h->graph_walk);
+    h->graph_build = h->graph_walk = nullptr;
+    h->graph_n = 0;
+}
+
 static int free_state(nb_sim* h)
 {
+    graphs_release(h);
     p2p_release(h);
     cudaFree(h->posw_buf[0]); cudaFree(h->posw_buf[1]);
     h->posw_buf[0] = h->posw_buf[1] = nullptr; h->posw = nullptr; h->posw_cur = 0;
@@ -135,8 +146,69 @@ int launch_allpairs(nb_sim* h)
 // `balanced`: Barnes-Hut inside nb_step with peer memory attached -- every rank walks an interleaved
 // share of ALL targets and stores into the owners' arrays; the exchange that follows makes sure this
 // rank's own accelerations are complete before the kick-drift reads them.
+// Captures `body` (launches on h->stream only) into an executable graph.
+template <typename F>
+static int capture_graph(nb_sim* h, cudaGraphExec_t* out, F body)
+{
+    cudaGraph_t g = nullptr;
+    NB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (rc != NB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    NB_CUDA(e);
+    const cudaError_t ei = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    NB_CUDA(ei);
+    return NB_OK;
+}
+
+static bool graphs_wanted(const nb_sim* h)
+{
+    static const bool enabled = [] { const char* v = std::getenv("NB_GRAPHS"); return v == nullptr || v[0] != '0'; }();
+    return enabled && !h->graph_failed && h->cfg.world == 1 && h->cfg.mode == NB_MODE_BARNESHUT && h->n <= ((size_t)1 << 21);
+}
+
+// The force pass of a small one-GPU Barnes-Hut step as two graph launches (same kernels, same order, same arguments).
+static int compute_forces_graphed(nb_sim* h)
+{
+    if (h->graph_build == nullptr || h->graph_n != h->n || h->graph_theta != h->cfg.theta)
+    {
+        graphs_release(h);
+        NB_CHECK(tree_reserve(h));                     // allocations and attribute calls happen outside the capture
+        const int before = h->last_launches;
+        int rc = capture_graph(h, &h->graph_build, [&] { return tree_build(h, false); });
+        if (rc == NB_OK) rc = capture_graph(h, &h->graph_walk, [&] { return tree_walk(h, false); });
+        h->graph_launches = h->last_launches - before;
+        h->last_launches = before;
+        if (rc != NB_OK)
+        {
+            graphs_release(h);
+            h->graph_failed = true;                    // this handle launches directly from now on
+            cudaGetLastError();
+            return rc;
+        }
+        h->graph_n = h->n;
+        h->graph_theta = h->cfg.theta;
+    }
+    cudaEvent_t* slot = h->ring[h->ring_pos % NB_TIMING_RING];
+    NB_CUDA(cudaEventRecord(slot[0], h->stream));
+    NB_CUDA(cudaGraphLaunch(h->graph_build, h->stream));
+    NB_CUDA(cudaEventRecord(slot[1], h->stream));
+    NB_CUDA(cudaGraphLaunch(h->graph_walk, h->stream));
+    NB_CUDA(cudaEventRecord(slot[2], h->stream));
+    ++h->ring_pos;
+    h->last_launches += h->graph_launches;
+    h->tree.built = true;
+    return NB_OK;
+}
+
 static int compute_forces(nb_sim* h, bool timed, bool balanced = false)
 {
+    if (timed && !balanced && graphs_wanted(h))
+    {
+        if (compute_forces_graphed(h) == NB_OK) return NB_OK;
+        // capture failed: fall through to direct launches
+    }
     cudaEvent_t* slot = h->ring[h->ring_pos % NB_TIMING_RING];
     if (timed) NB_CUDA(cudaEventRecord(slot[0], h->stream));
     if (h->cfg.mode == NB_MODE_ALLPAIRS)
@@ -707,6 +779,14 @@ int nb_seed_collision_device(nb_handle h, size_t n, uint64_t seed, float scale, 
     NB_CUDA(cudaSetDevice(h->cfg.device));
     NB_CHECK(set_bodies(h, n));
     return nb::seed_collision_device(h, n, seed, scale, separation, approach_speed);
+}
+
+int nb_enable_graphs(nb_handle h, int on)
+{
+    NB_REQUIRE(h != nullptr, NB_ERR_ARG, "null handle");
+    h->graph_failed = (on == 0);
+    if (!on) graphs_release(h);
+    return NB_OK;
 }
 
 int nb_scale_masses(nb_handle h, double factor)

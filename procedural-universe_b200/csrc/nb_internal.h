@@ -126,6 +126,14 @@ struct nb_sim
     // recorded every step without a host sync, read back after the timed region (nb_step_timing_mean)
     cudaEvent_t ring[NB_TIMING_RING][3] = {};
     unsigned long long ring_pos = 0;          // force passes recorded so far
+    // Small scenes (one GPU, Barnes-Hut): the ~40 launches of a step are replayed as two CUDA graphs -- tree build and
+    // walk -- captured once per (body count, theta); the reference's own range is <= 50 000 bodies (UI.cpp:75), where
+    // a step is launch-bound
+    cudaGraphExec_t graph_build = nullptr, graph_walk = nullptr;
+    size_t graph_n = 0;
+    float graph_theta = 0.f;
+    int graph_launches = 0;
+    bool graph_failed = false;
     bool timing_valid = false;
     int last_launches = 0;
     unsigned long long total_launches = 0;

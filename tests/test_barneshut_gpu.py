@@ -446,3 +446,24 @@ def test_walk_occupancy_histogram_is_consistent_with_the_counters(pkg, galaxy):
     assert int((h * np.arange(33, dtype=np.uint64)).sum()) == st["visits"]
     assert h[0] == 0 and h.sum() >= st["visits"] // 32
     sim.close()
+
+
+@pytest.mark.parametrize("n", [4000, 50000])
+def test_graph_replay_of_small_steps_is_bitwise_the_direct_launches(pkg, n):
+    """One-GPU Barnes-Hut steps of small scenes replay their launches as CUDA graphs (csrc/nb_api.cu,
+    compute_forces_graphed): same kernels and arguments, so the state after 20 steps must be bitwise the state the
+    directly launched steps produce -- also across a theta change (the graphs are re-captured)."""
+    p = pkg.seed_galaxy_host(n, 11, 1.0)
+    hashes = []
+    for graphs in (True, False):
+        sim = bh(pkg, theta=0.5)
+        sim.enable_graphs(graphs)
+        sim.init(p)
+        sim.step(0.02 / 60, 10)
+        sim.set_theta(0.8)
+        sim.step(0.02 / 60, 10)
+        hashes.append(sim.state_hash())
+        launches = sim.last_step_timing()[2]
+        sim.close()
+    assert hashes[0] == hashes[1]
+    assert launches > 300          # 10 steps x ~40 kernels are counted either way
