@@ -537,6 +537,7 @@ def run_workload(ctx, name, steps, warmup, headline):
     # CUDA events recorded by the library on the launching stream around the dominant kernel and the tree build of
     # every step (a ring of 64), read only now
     kms, build_ms, timed_steps = sim.step_timing_mean(steps)
+    period_ms = sim.step_period_mean(steps)[0] if steps > 1 else None
     launches = sim.last_step_timing()[2] * steps
 
     if energy is not None:
@@ -608,6 +609,7 @@ def run_workload(ctx, name, steps, warmup, headline):
         "peak_probe": probe, "frac_of_probe": achieved / probe,
         "flops_per_interaction": FLOPS_PER_INTERACTION, "interactions_per_launch": evals,
         "kernel_ms": kms, "kernel_ms_steps_averaged": timed_steps, "kernel_share_of_step": kms * steps / total_ms,
+        "step_ms_same_steps": period_ms,
     }
     if wl["mode"] == "bh":
         build_bytes = float(n) * BUILD_BYTES_PER_BODY

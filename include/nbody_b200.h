@@ -308,6 +308,9 @@ NB_API int nb_last_step_timing(nb_handle h, float* total_ms, float* force_kernel
  * the library records three CUDA events per step on the handle's stream and reads them only here, so a
  * timed loop needs no host synchronisation between steps. */
 NB_API int nb_step_timing_mean(nb_handle h, int max_steps, float* force_kernel_ms, float* build_ms, int* steps_averaged);
+/* Mean period of the last steps on the device: from the begin of one force pass to the begin of the next (force
+ * pass + kick-drift + exchange + whatever the caller put between the steps), over the same ring of events. */
+NB_API int nb_step_period_mean(nb_handle h, int max_steps, float* period_ms, int* steps_averaged);
 /* Barnes-Hut: device time of the tree build (Morton + sort + Karras + reduction) of that step;
  * force_kernel_ms above is then the traversal alone.  0 in all-pairs mode. */
 NB_API int nb_last_build_timing(nb_handle h, float* build_ms);

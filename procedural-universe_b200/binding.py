@@ -133,6 +133,7 @@ def load():
     L.nb_p2p_attach_local.argtypes = [vp, C.POINTER(vp)]
     L.nb_last_step_timing.argtypes = [vp, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int)]
     L.nb_step_timing_mean.argtypes = [vp, C.c_int, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int)]
+    L.nb_step_period_mean.argtypes = [vp, C.c_int, C.POINTER(f32), C.POINTER(C.c_int)]
     L.nb_probe_fp32_peak.argtypes = [vp, C.POINTER(f64)]
     L.nb_last_build_timing.argtypes = [vp, C.POINTER(f32)]
     L.nb_shard_range.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]
@@ -461,6 +462,12 @@ class Sim:
         a, b, k = C.c_float(), C.c_float(), C.c_int()
         _check(self._L.nb_step_timing_mean(self._h, max_steps, C.byref(a), C.byref(b), C.byref(k)))
         return a.value, b.value, k.value
+
+    def step_period_mean(self, max_steps=0):
+        """(mean device period of the last steps in ms, steps averaged)."""
+        a, k = C.c_float(), C.c_int()
+        _check(self._L.nb_step_period_mean(self._h, max_steps, C.byref(a), C.byref(k)))
+        return a.value, k.value
 
     def last_build_ms(self):
         t = C.c_float()

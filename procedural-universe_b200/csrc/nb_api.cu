@@ -738,6 +738,22 @@ int nb_step_timing_mean(nb_handle h, int max_steps, float* force_kernel_ms, floa
     return NB_OK;
 }
 
+int nb_step_period_mean(nb_handle h, int max_steps, float* period_ms, int* steps_averaged)
+{
+    NB_REQUIRE(h != nullptr && period_ms != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->timing_valid && h->ring_pos > 1, NB_ERR_STATE, "fewer than two timed force passes");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CUDA(cudaEventSynchronize(h->ev[1]));
+    unsigned long long k = h->ring_pos < (unsigned long long)NB_TIMING_RING ? h->ring_pos : (unsigned long long)NB_TIMING_RING;
+    if (max_steps > 0 && (unsigned long long)max_steps < k) k = (unsigned long long)max_steps;
+    NB_REQUIRE(k > 1, NB_ERR_STATE, "fewer than two timed force passes");
+    float ms = 0.f;
+    NB_CUDA(cudaEventElapsedTime(&ms, h->ring[(h->ring_pos - k) % NB_TIMING_RING][0], h->ring[(h->ring_pos - 1) % NB_TIMING_RING][0]));
+    *period_ms = ms / (float)(k - 1);
+    if (steps_averaged) *steps_averaged = (int)(k - 1);
+    return NB_OK;
+}
+
 int nb_last_build_timing(nb_handle h, float* build_ms)
 {
     NB_REQUIRE(h != nullptr && build_ms != nullptr, NB_ERR_ARG, "null argument");

@@ -177,7 +177,7 @@ int preload_step_kernels(nb_sim* h);
 int tree_reserve(nb_sim* h);
 void tree_release(nb_sim* h);
 int tree_build(nb_sim* h, bool collective = false);
-int tree_walk(nb_sim* h, bool balanced = false);
+int tree_walk(nb_sim* h, bool balanced = false, bool instrumented = false);
 
 // nccl_dl.cpp
 int comm_unique_id(uint8_t id[128]);

@@ -22,6 +22,7 @@
 // Determinism: the sort is a stable LSD radix sort, the tree is a pure function of the sorted
 // keys, and the bottom-up pass adds (left + right) in fp64 -- no order-dependent atomics -- so
 // every rank that holds the same positions builds bit-identical trees.
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -1002,12 +1003,12 @@ int tree_reserve(nb_sim* h)
     // Opt in to > 48 KB of dynamic shared memory once per device, here (Init time) and not in the step:
     // the call can wait for the device to drain, which must never happen while another handle of this
     // process sits in a peer-flag wait (several ranks driven by one host thread).
-    static bool opted_in[64] = {};
+    static std::atomic<bool> opted_in[64];
     const int dev = h->cfg.device;
-    if (dev < 0 || dev >= 64 || !opted_in[dev])
+    if (dev < 0 || dev >= 64 || !opted_in[dev].load(std::memory_order_acquire))
     {
         NB_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
-        if (dev >= 0 && dev < 64) opted_in[dev] = true;
+        if (dev >= 0 && dev < 64) opted_in[dev].store(true, std::memory_order_release);    // idempotent: a second caller repeats it at worst
     }
     if (t.capacity >= n) return NB_OK;
     tree_release(h);
@@ -1129,9 +1130,7 @@ int tree_build(nb_sim* h, bool collective)
     return NB_OK;
 }
 
-static bool g_walk_stats = false;
-
-int tree_walk(nb_sim* h, bool balanced)
+int tree_walk(nb_sim* h, bool balanced, bool g_walk_stats)
 {
     TreeBuffers& t = h->tree;
     const int n = (int)h->n;
@@ -1334,10 +1333,7 @@ int nb_get_walk_stats(nb_handle h, uint64_t stats3[3])
     NB_REQUIRE(h->exchanged, NB_ERR_STATE, "positions of remote ranks are stale");
     if (h->p2p_attached) NB_CHECK(p2p_wait(h));      // the peers' positions of the last step are in
     NB_CHECK(tree_build(h));
-    g_walk_stats = true;
-    const int rc = tree_walk(h);
-    g_walk_stats = false;
-    NB_CHECK(rc);
+    NB_CHECK(tree_walk(h, false, true));
     NB_CUDA(cudaStreamSynchronize(h->stream));
     unsigned long long s[3];
     NB_CUDA(cudaMemcpy(s, h->tree.stats, sizeof(s), cudaMemcpyDeviceToHost));
