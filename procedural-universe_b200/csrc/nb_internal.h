@@ -68,6 +68,7 @@ struct TreeBuffers
     int cur = 0;                    // which ping-pong half holds the sorted result
     size_t n_inbounds_host = 0;
     bool built = false;
+    bool split_ids = false;         // internal node ids are split positions (k_build_up), not Karras's range ends
 };
 
 }  // namespace nb

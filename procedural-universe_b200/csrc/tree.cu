@@ -25,6 +25,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,7 +41,7 @@ constexpr int kEnd = -1;
 constexpr int kWalkStatWords = 3 + 33;   // {cells, pairs, visits} + lane-occupancy histogram [0..32]
 
 // counters[] slots
-enum { C_INBOUNDS = 0, C_TOTAL = 1, C_SEG = 2, C_SEG_OOB = 3, C_WORDS = 8 };   // C_SEG: bodies this rank sorts (sharded sort), C_SEG_OOB: of which outside the cube
+enum { C_INBOUNDS = 0, C_TOTAL = 1, C_SEG = 2, C_SEG_OOB = 3, C_ROOT = 4, C_WORDS = 8 };   // C_SEG: bodies this rank sorts (sharded sort), C_SEG_OOB: of which outside the cube
 
 // ------------------------------------------------------------------------------------------------
 // K3: Morton codes.  Same cells as the comparison descent of the CPU restatement (oracle/nbody_port.c,
@@ -467,6 +468,103 @@ k_bottom_up(const float4* __restrict__ posw, const unsigned int* __restrict__ or
         if (up == kEnd) return;
         id = node;
         node = up;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 + K6 fused (NB_BUILD=agglomerative; measured slower than the two passes, kept with its tests): agglomerative construction (Apetrei, "Fast and Simple Agglomerative LBVH Construction",
+// 2014) -- the radix tree is found WHILE its sums are reduced, bottom-up, instead of by two binary searches per
+// node beforehand.  A thread starts at a leaf with the range [j, j]; a finished range [l, r] joins the neighbour
+// it shares the longer prefix with: the node that splits at r (range becomes its LEFT child) or at l - 1 (its
+// RIGHT child).  The two children of a node meet through one 64-bit exchange word {outer bound, node id}: the
+// first to arrive leaves its half and retires, the second takes it, adds the sibling's sums to the ones it
+// carries in registers, writes the node (children, parent links, prefix, first slot, the children's octree level
+// and "owns a cell" bit, the owning-node counts -- everything k_karras wrote) and climbs on.  Internal node ids are
+// SPLIT POSITIONS here (k_karras numbers a node by an end of its range); it is the same tree, and nb_get_tree
+// renumbers for the topology parity hook.  The root's id is left in counters[C_ROOT].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_build_up(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned long long* __restrict__ keys,
+           unsigned int* __restrict__ counters, int leaf_base, int2* __restrict__ child, int* __restrict__ prefix,
+           int* __restrict__ parent, int* __restrict__ first_slot, unsigned short* __restrict__ meta, unsigned int* __restrict__ cnt,
+           unsigned long long* meet, double* nsum)
+{
+    const int m = (int)counters[C_INBOUNDS];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m || m < 2) return;
+    int l = j, r = j, id = leaf_base + j;
+    double w, sx, sy, sz;
+    {
+        const float4 p = posw[order[j]];
+        w = (double)p.w;
+        sx = w * (double)p.x; sy = w * (double)p.y; sz = w * (double)p.z;
+    }
+    for (;;)
+    {
+        if (l == 0 && r == m - 1)
+        {
+            parent[id] = kEnd;
+            meta[id] = (unsigned short)level_of(delta_fn(keys, m, l, r)) | kOwns;
+            atomicAdd(&cnt[0], 1u);
+            counters[C_ROOT] = (unsigned int)id;
+            return;
+        }
+        // longer common prefix = closer; at the ends of the key list there is only one neighbour
+        const int dl = l > 0 ? delta_fn(keys, m, l - 1, l) : -1;
+        const int dr = r < m - 1 ? delta_fn(keys, m, r, r + 1) : -1;
+        const bool to_right = dr > dl;                   // the node splitting at r: this range is its left child
+        const int node = to_right ? r : l - 1;
+        const unsigned long long mine = ((unsigned long long)(unsigned int)(to_right ? l : r) << 32) | (unsigned int)id;
+        // Release (internal ranges) publishes the sums record this thread stored when it formed `id`; a leaf has stored
+        // nothing.  No acquire half: the sibling's record is read with ld.global.cg after the branch on `other`
+        // (same reasoning as k_bottom_up).
+        unsigned long long other;
+        if (id >= leaf_base)
+            asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(other) : "l"(meet + node), "l"(mine) : "memory");
+        else
+            asm volatile("atom.release.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(other) : "l"(meet + node), "l"(mine) : "memory");
+        if (other == ~0ull) return;                       // first arrival: the sibling range is not finished
+        const int sib = (int)(unsigned int)(other & 0xffffffffull);
+        const int bound = (int)(unsigned int)(other >> 32);
+        double ow, ox, oy, oz;
+        if (sib >= leaf_base)
+        {
+            const float4 p = posw[order[sib - leaf_base]];
+            ow = (double)p.w;
+            ox = ow * (double)p.x; oy = ow * (double)p.y; oz = ow * (double)p.z;
+        }
+        else
+        {
+            const double2* rec = reinterpret_cast<const double2*>(nsum + 4 * (size_t)sib);
+            const double2 a = __ldcg(rec), b = __ldcg(rec + 1);
+            ow = a.x; ox = a.y; oy = b.x; oz = b.y;
+        }
+        w += ow; sx += ox; sy += oy; sz += oz;           // fp64 addition commutes: left + right either way
+        double2* rec = reinterpret_cast<double2*>(nsum + 4 * (size_t)node);
+        rec[0] = make_double2(w, sx);
+        rec[1] = make_double2(sy, sz);
+        const int cl = to_right ? id : sib, cr = to_right ? sib : id;
+        if (to_right) r = bound; else l = bound;
+        const int dnode = delta_fn(keys, m, l, r);
+        const int level = level_of(dnode);
+        child[node] = make_int2(cl, cr);
+        prefix[node] = dnode;
+        first_slot[node] = l;
+        parent[cl] = node;
+        parent[cr] = node;
+        if (cl < leaf_base)
+        {
+            const int lc = level_of(delta_fn(keys, m, l, node));
+            meta[cl] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0);
+            if (lc > level) atomicAdd(&cnt[l], 1u);
+        }
+        if (cr < leaf_base)
+        {
+            const int lc = level_of(delta_fn(keys, m, node + 1, r));
+            meta[cr] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0);
+            if (lc > level) atomicAdd(&cnt[node + 1], 1u);
+        }
+        id = node;
     }
 }
 
@@ -1108,9 +1206,27 @@ int tree_build(nb_sim* h, bool collective)
     const int leaf_base = n;
     const int words = n + 1;
     NB_CUDA(cudaMemsetAsync(t.cnt, 0, (size_t)words * sizeof(unsigned int), st));
-    k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.skeys, t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range,
-                                                t.meta, t.cnt);
-    k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.svals, t.counters, leaf_base, t.child, t.parent, t.flags, t.nsum);
+    // NB_BUILD=agglomerative selects the fused construction + reduction (k_build_up).  Measured at 16 M bodies it is
+    // SLOWER than the two passes (2.07 ms against 0.53 + 0.98 ms): every level of its climb waits for the neighbour
+    // keys of a range it has only just learnt, on top of the exchange and the sibling record, where k_karras's binary
+    // searches run at full occupancy and k_bottom_up's climb carries only three dependent accesses per level.
+    static const bool two_pass = [] { const char* v = std::getenv("NB_BUILD"); return v == nullptr || std::strcmp(v, "agglomerative") != 0; }();
+    t.split_ids = !two_pass;
+    if (two_pass)
+    {
+        // Karras's two binary searches per node, then the reduction
+        k_karras<<<blocks_for(n, 256), 256, 0, st>>>(t.skeys, t.counters, leaf_base, t.child, t.prefix, t.parent, t.flags, t.range,
+                                                    t.meta, t.cnt);
+        k_bottom_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.svals, t.counters, leaf_base, t.child, t.parent, t.flags, t.nsum);
+    }
+    else
+    {
+        // the sort's spare ping-pong half is free now: the children's meeting words live there
+        unsigned long long* meet = t.keys[t.cur ^ 1];
+        NB_CUDA(cudaMemsetAsync(meet, 0xFF, (size_t)n * sizeof(unsigned long long), st));
+        k_build_up<<<blocks_for(n, 256), 256, 0, st>>>(h->posw, t.svals, t.skeys, t.counters, leaf_base, t.child, t.prefix, t.parent, t.range,
+                                                      t.meta, t.cnt, meet, t.nsum);
+    }
     // pre-order ranks: owning nodes per first slot were counted by k_karras; exclusive scan, rank, then the records
     {
         const int sblocks = (words + 4095) / 4096;
@@ -1213,6 +1329,7 @@ int preload_tree()
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_karras)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_bottom_up)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_build_up)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_scan_apply)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rank)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_finalize)));
@@ -1271,27 +1388,45 @@ int nb_get_tree(nb_handle h, int32_t* left, int32_t* right, int32_t* prefix_bits
     if (k == 0) return NB_OK;
     const size_t n = h->n;
     const int leaf_base = (int)n;
-    if (left || right)
+    std::vector<int2> ch(k);
+    NB_CUDA(cudaMemcpy(ch.data(), h->tree.child, k * sizeof(int2), cudaMemcpyDeviceToHost));
+    // Node ids of the parity hook are Karras's (a node is numbered by an end of its range: a left child by its last
+    // slot, a right child by its first, the root 0).  k_build_up numbers a node by its split position: the left
+    // child of the node splitting at g is then Karras's node g, the right child g + 1.
+    std::vector<int> kid(k);
+    if (h->tree.split_ids)
     {
-        std::vector<int2> tmp(k);
-        NB_CUDA(cudaMemcpy(tmp.data(), h->tree.child, k * sizeof(int2), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < k; ++i)
-        {
-            if (left) left[i] = tmp[i].x >= leaf_base ? ~(tmp[i].x - leaf_base) : tmp[i].x;
-            if (right) right[i] = tmp[i].y >= leaf_base ? ~(tmp[i].y - leaf_base) : tmp[i].y;
-        }
+        std::vector<int> par(k);
+        NB_CUDA(cudaMemcpy(par.data(), h->tree.parent, k * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t v = 0; v < k; ++v) kid[v] = par[v] == kEnd ? 0 : (ch[(size_t)par[v]].x == (int)v ? par[v] : par[v] + 1);
     }
-    if (prefix_bits) NB_CUDA(cudaMemcpy(prefix_bits, h->tree.prefix, k * sizeof(int), cudaMemcpyDeviceToHost));
+    else
+        for (size_t v = 0; v < k; ++v) kid[v] = (int)v;
+    if (left || right)
+        for (size_t v = 0; v < k; ++v)
+        {
+            const int cl = ch[v].x, cr = ch[v].y;
+            const int il = h->tree.split_ids ? (int)v : cl, ir = h->tree.split_ids ? (int)v + 1 : cr;     // Karras ids of internal children
+            if (left) left[kid[v]] = cl >= leaf_base ? ~(cl - leaf_base) : il;
+            if (right) right[kid[v]] = cr >= leaf_base ? ~(cr - leaf_base) : ir;
+        }
+    if (prefix_bits)
+    {
+        std::vector<int> pf(k);
+        NB_CUDA(cudaMemcpy(pf.data(), h->tree.prefix, k * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t v = 0; v < k; ++v) prefix_bits[kid[v]] = pf[v];
+    }
     if (mass || com3)
     {
         std::vector<double> s4(4 * k);
         NB_CUDA(cudaMemcpy(s4.data(), h->tree.nsum, 4 * k * sizeof(double), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < k; ++i)
+        for (size_t v = 0; v < k; ++v)
         {
-            const double w = s4[4 * i];
+            const double w = s4[4 * v];
+            const size_t i = (size_t)kid[v];
             if (mass) mass[i] = w / h->cfg.G;
             if (com3)
-                for (int c = 0; c < 3; ++c) com3[3 * i + c] = (float)(w != 0.0 ? s4[4 * i + 1 + c] / w : 0.0);
+                for (int c = 0; c < 3; ++c) com3[3 * i + c] = (float)(w != 0.0 ? s4[4 * v + 1 + c] / w : 0.0);
         }
     }
     return NB_OK;

@@ -467,3 +467,34 @@ def test_graph_replay_of_small_steps_is_bitwise_the_direct_launches(pkg, n):
         sim.close()
     assert hashes[0] == hashes[1]
     assert launches > 300          # 10 steps x ~40 kernels are counted either way
+
+
+def test_agglomerative_build_gives_the_same_tree_and_forces(pkg):
+    """NB_BUILD=agglomerative (k_build_up: construction fused with the reduction, nodes numbered by split position)
+    must produce the tree of the default two-pass build: same topology through nb_get_tree's renumbering, same node
+    sums, bitwise the same accelerations.  Runs in a child process because the switch is read once per process."""
+    import json, os, subprocess, sys
+    from conftest import ROOT
+    code = r"""
+import importlib, json, sys, hashlib
+import numpy as np
+sys.path.insert(0, %r)
+pkg = importlib.import_module("procedural-universe_b200")
+p = pkg.seed_galaxy_host(30011, 5, 1.0)
+sim = pkg.Sim(mode=pkg.MODE_BARNESHUT, theta=0.5)
+sim.init(p)
+t = sim.tree()
+acc = sim.accelerations()
+h = hashlib.sha256()
+for k in ("left", "right", "prefix", "mass", "com"):
+    h.update(np.ascontiguousarray(t[k]).tobytes())
+h.update(acc.tobytes())
+sim.step(0.02 / 60, 5)
+print(json.dumps({"tree_and_acc": h.hexdigest(), "state": sim.state_hash()}))
+""" % ROOT
+    out = []
+    for build in ("karras", "agglomerative"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, NB_BUILD=build))
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert out[0] == out[1]

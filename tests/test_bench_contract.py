@@ -29,3 +29,16 @@ def test_reference_arm_other_ranks_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_times_a_whole_barneshut_update():
+    """The Barnes-Hut reference arm is one BarnesHut::Update on the reference's own thread pool (not a one-thread
+    sample), seeded through oracle/_ref: the product library is never loaded on that arm."""
+    r = subprocess.run([sys.executable, "-X", "importtime", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "bh_50k",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert line["impl"] == "reference" and line["value"] > 1e5
+    assert "procedural-universe_b200" not in r.stderr          # -X importtime lists every module imported
+    if line["cpu_baseline"]["kind"] == "reference":
+        assert "BarnesHut::Update" in line["cpu_baseline"]["sample"] and line["cpu_baseline"]["cores"] >= 1

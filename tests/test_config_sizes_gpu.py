@@ -162,3 +162,28 @@ def test_collision_1m_energy_and_trajectories_track_the_reference(pkg):
     vrel = np.linalg.norm(q["Velocity"][::stride] - g["final_vel_sample"], axis=1) / np.linalg.norm(g["final_vel_sample"], axis=1)
     assert np.median(vrel) < 1e-3
     sim.close()
+
+
+def test_mass_scaling_and_step_timers(pkg):
+    """nb_scale_masses re-derives the device state from the scaled image: accelerations scale with the factor (to
+    fp32 rounding of G m), energies with its square / first power; the event-ring timers report after a timed loop."""
+    n = 20000
+    p = pkg.seed_collision_host(n, 42, 1.0, **COLLISION)
+    a = pkg.Sim(mode=pkg.MODE_BARNESHUT, theta=0.5)
+    a.init(p)
+    acc0 = a.accelerations()
+    a.scale_masses(1.0 / 64)
+    acc1 = a.accelerations()
+    assert rel_err(acc1 * 64, acc0).max() < 1e-5
+    q = p.copy()
+    q["Mass"] *= 1.0 / 64
+    b = pkg.Sim(mode=pkg.MODE_BARNESHUT, theta=0.5)
+    b.init(q)
+    assert np.array_equal(b.accelerations(), acc1)           # same state as initialising with the scaled masses
+    for _ in range(5):
+        a.step(0.02 / 60, 1)
+    kernel_ms, build_ms, k = a.step_timing_mean(4)
+    period_ms, kp = a.step_period_mean(4)
+    assert k == 4 and kp == 3 and 0 < kernel_ms < period_ms and 0 < build_ms < period_ms
+    a.close()
+    b.close()
