@@ -47,7 +47,8 @@ struct TreeBuffers
     int2* child = nullptr;          // [n-1] {left, right} child of internal node (< n internal, >= n leaf slot + n)
     int32_t* parent = nullptr;      // [2n-1]   parent of internal nodes then of leaves
     int32_t* prefix = nullptr;      // [n-1]    common-prefix length in bits (0..63; 64+ = duplicate codes)
-    int32_t* range = nullptr;       // [2][n-1] first/last sorted slot covered
+    int32_t* range = nullptr;       // [n-1] first sorted slot covered
+    int32_t* range_hi = nullptr;    // [n-1] last sorted slot covered
     uint32_t* flags = nullptr;      // [n-1]    arrival counters of the bottom-up pass
     double* nsum = nullptr;         // [n-1][4] {G M, G M x, G M y, G M z} of internal nodes, fp64, one 32-byte record each
     float4* walk_a = nullptr;       // [2n-1] {com.x, com.y, com.z, G*M}
