@@ -43,6 +43,8 @@ struct TreeBuffers
     unsigned int* vals[2] = {nullptr, nullptr};         // body index per slot, ping-pong
     uint32_t* hist = nullptr;       // radix-sort block histograms
     size_t hist_words = 0;
+    uint32_t* desc = nullptr;       // onesweep: [8][tiles][256] tile descriptors + [8][256] digit counts + 8 tickets
+    size_t desc_words = 0;
     uint32_t* counters = nullptr;   // [0] in-bounds bodies, [1..] scratch
     int2* child = nullptr;          // [n-1] {left, right} child of internal node (< n internal, >= n leaf slot + n)
     int32_t* parent = nullptr;      // [2n-1]   parent of internal nodes then of leaves

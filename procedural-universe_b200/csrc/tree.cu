@@ -224,6 +224,57 @@ __global__ void __launch_bounds__(256) k_rs_scan_totals(unsigned int* __restrict
     totals[threadIdx.x] = s[threadIdx.x];
 }
 
+// Onesweep-style sort (Adinets & Merrill 2022), NB_SORT=onesweep: ONE histogram pass counts all eight digits of every key,
+// and the scatter of pass p finds "keys of my digit in the tiles before mine" by decoupled look-back over per-tile
+// descriptors (2 flag bits + 30-bit count) instead of a histogram kernel and two scan kernels per pass.  Tiles are
+// handed out by an atomic ticket, so a tile only ever waits for tiles whose blocks are already running.
+// Measured at 16 M bodies: it removes 8 x 61 us of histogram + scan launches and adds 80 us of one-off histogram plus
+// ~50 us of look-back per pass (one thread per digit walks back through the ~440 resident tiles, eight entries per
+// round trip) -- 1.75 ms either way, so the three-kernel passes stay the default; a warp-parallel look-back is what
+// it would take to turn the saved launches into time.
+constexpr int RS_PASSES = 8;
+constexpr unsigned int RS_FLAG_LOCAL = 1u << 30, RS_FLAG_PREFIX = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(256)
+k_rs_hist_all(const unsigned long long* __restrict__ keys, int n, const unsigned int* __restrict__ n_dev, unsigned int* __restrict__ ghist)
+{
+    if (n_dev != nullptr) n = (int)*n_dev;
+    __shared__ unsigned int h[RS_PASSES][256];
+    for (int k = threadIdx.x; k < RS_PASSES * 256; k += 256) (&h[0][0])[k] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * 256)
+    {
+        const unsigned long long key = keys[i];
+#pragma unroll
+        for (int p = 0; p < RS_PASSES; ++p) atomicAdd(&h[p][(unsigned int)(key >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < RS_PASSES * 256; k += 256)
+    {
+        const unsigned int v = (&h[0][0])[k];
+        if (v) atomicAdd(&ghist[k], v);
+    }
+}
+
+// one block: ghist[p][d] -> exclusive prefix over d, for every pass p
+__global__ void __launch_bounds__(256) k_rs_scan_all(unsigned int* __restrict__ ghist)
+{
+    __shared__ unsigned int s[256];
+    for (int p = 0; p < RS_PASSES; ++p)
+    {
+        s[threadIdx.x] = ghist[p * 256 + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned int run = 0;
+            for (int d = 0; d < 256; ++d) { const unsigned int v = s[d]; s[d] = run; run += v; }
+        }
+        __syncthreads();
+        ghist[p * 256 + threadIdx.x] = s[threadIdx.x];
+        __syncthreads();
+    }
+}
+
 // Scatter of one tile.  (1) every key gets its rank among the keys of the same digit that precede
 // it in the tile (warp-level match.any per round + running per-warp counters; the order is warp,
 // round, lane = input order, so the sort is stable); (2) the tile is reordered by digit in shared
@@ -233,14 +284,24 @@ __global__ void __launch_bounds__(256) k_rs_scan_totals(unsigned int* __restrict
 constexpr size_t RS_SCATTER_SMEM = RS_TILE * (sizeof(unsigned long long) + sizeof(unsigned int) + sizeof(unsigned short)) +
                                    (RS_WARPS + 2) * 256 * sizeof(unsigned int);
 
+template <bool ONESWEEP>
 __global__ void __launch_bounds__(RS_THREADS, 3)
 k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
              unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n, int shift,
              const unsigned int* __restrict__ hist, const unsigned int* __restrict__ totals, int tiles,
-             const unsigned int* __restrict__ n_dev)
+             const unsigned int* __restrict__ n_dev, unsigned int* desc = nullptr, unsigned int* ticket = nullptr)
 {
+    // desc != nullptr: onesweep -- `totals` holds this pass's exclusive digit offsets, the tile index comes from the
+    // ticket, and the per-tile prefix from look-back over desc[tile][digit]
     if (n_dev != nullptr) n = (int)*n_dev;
-    if (blockIdx.x * RS_TILE >= n) return;
+    __shared__ int tile_id;
+    if (ONESWEEP)
+    {
+        if (threadIdx.x == 0) tile_id = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+    }
+    const int tile = ONESWEEP ? tile_id : (int)blockIdx.x;
+    if ((long long)tile * RS_TILE >= n) return;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(rs_smem);            // tile, input order
     unsigned int* svals = reinterpret_cast<unsigned int*>(skeys + RS_TILE);
@@ -253,7 +314,7 @@ k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int*
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
 
-    const int tile_base = blockIdx.x * RS_TILE;
+    const int tile_base = tile * RS_TILE;
     const int wbase = warp * (RS_ITEMS * 32);    // warp w owns input slots [512 w, 512 w + 512)
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
@@ -301,7 +362,36 @@ k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int*
         for (int w = 0; w < warp; ++w) wprefix += warp_tot[w];
         const unsigned int first = wprefix + x - run;
         lbase[d] = first;
-        gbase[d] = totals[d] + hist[(size_t)d * tiles + blockIdx.x] - first;
+        unsigned int before;                      // keys of digit d in the tiles before this one
+        if (ONESWEEP)
+        {
+            volatile unsigned int* dd = desc + d;
+            dd[(size_t)tile * 256] = RS_FLAG_LOCAL | run;
+            before = 0;
+            // look back eight tiles per round trip: the loads of a batch are independent; the batch is then consumed
+            // nearest tile first, re-reading an entry that was not published yet
+            for (int t = tile - 1; t >= 0;)
+            {
+                constexpr int LB = 8;
+                unsigned int v[LB];
+#pragma unroll
+                for (int k = 0; k < LB; ++k) v[k] = t - k >= 0 ? dd[(size_t)(t - k) * 256] : (2u << 30);
+                bool done = false;
+#pragma unroll
+                for (int k = 0; k < LB; ++k)
+                {
+                    if (done) continue;
+                    while ((v[k] >> 30) == 0u) v[k] = dd[(size_t)(t - k) * 256];
+                    before += v[k] & RS_VALUE_MASK;
+                    done = (v[k] >> 30) == 2u;
+                }
+                if (done) break;
+                t -= LB;
+            }
+            dd[(size_t)tile * 256] = RS_FLAG_PREFIX | (before + run);
+        }
+        else before = hist[(size_t)d * tiles + tile];
+        gbase[d] = totals[d] + before - first;
     }
     __syncthreads();
 #pragma unroll
@@ -1184,7 +1274,7 @@ void tree_release(nb_sim* h)
 {
     TreeBuffers& t = h->tree;
     for (int k = 0; k < 2; ++k) { cudaFree(t.keys[k]); cudaFree(t.vals[k]); t.keys[k] = nullptr; t.vals[k] = nullptr; }
-    cudaFree(t.hist); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
+    cudaFree(t.hist); cudaFree(t.desc); cudaFree(t.counters); cudaFree(t.child); cudaFree(t.parent); cudaFree(t.prefix);
     cudaFree(t.range); cudaFree(t.range_hi); cudaFree(t.flags); cudaFree(t.nsum); cudaFree(t.walk_a);
     cudaFree(t.walk_b); cudaFree(t.stats); cudaFree(t.cnt); cudaFree(t.pref); cudaFree(t.rank); cudaFree(t.tlist); cudaFree(t.meta);
     cudaFree(t.keys_final); cudaFree(t.vals_final); cudaFree(t.splitters);
@@ -1202,7 +1292,8 @@ int tree_reserve(nb_sim* h)
     const int dev = h->cfg.device;
     if (dev < 0 || dev >= 64 || !opted_in[dev].load(std::memory_order_acquire))
     {
-        NB_CUDA(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+        NB_CUDA(cudaFuncSetAttribute(k_rs_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+        NB_CUDA(cudaFuncSetAttribute(k_rs_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
         if (dev >= 0 && dev < 64) opted_in[dev].store(true, std::memory_order_release);    // idempotent: a second caller repeats it at worst
     }
     if (t.capacity >= n) return NB_OK;
@@ -1214,6 +1305,9 @@ int tree_reserve(nb_sim* h)
         NB_CUDA(cudaMalloc(&t.vals[k], n * sizeof(unsigned int)));
     }
     t.hist_words = 256 * tiles + 256 + tiles + 16;
+    // onesweep: per-pass tile descriptors [8][tiles][256], then the 8 x 256 digit counts, then 8 tickets
+    t.desc_words = (size_t)RS_PASSES * tiles * 256 + RS_PASSES * 256 + 16;
+    NB_CUDA(cudaMalloc(&t.desc, t.desc_words * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.hist, t.hist_words * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.counters, C_WORDS * sizeof(unsigned int)));
     NB_CUDA(cudaMalloc(&t.child, n * sizeof(int2)));
@@ -1269,16 +1363,38 @@ int tree_build(nb_sim* h, bool collective)
         src = 1;
         n_dev = t.counters + C_SEG;
     }
-    for (int pass = 0; pass < 8; ++pass)
+    static const bool three_kernel_sort = [] { const char* v = std::getenv("NB_SORT"); return v == nullptr || std::strcmp(v, "onesweep") != 0; }();
+    if (three_kernel_sort || (size_t)n >= ((size_t)1 << 30))
     {
-        const int shift = 8 * pass;
-        k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], n, shift, t.hist, tiles, n_dev);
-        k_rs_scan_rows<<<256, 256, 0, st>>>(t.hist, tiles, totals, n_dev);
-        k_rs_scan_totals<<<1, 256, 0, st>>>(totals);
-        k_rs_scatter<<<tiles, RS_THREADS, RS_SCATTER_SMEM, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, shift,
-                                                                t.hist, totals, tiles, n_dev);
-        h->last_launches += 4;
-        src ^= 1;
+        // per pass a histogram kernel, two scan kernels and the scatter
+        for (int pass = 0; pass < 8; ++pass)
+        {
+            const int shift = 8 * pass;
+            k_rs_hist<<<tiles, RS_THREADS, 0, st>>>(t.keys[src], n, shift, t.hist, tiles, n_dev);
+            k_rs_scan_rows<<<256, 256, 0, st>>>(t.hist, tiles, totals, n_dev);
+            k_rs_scan_totals<<<1, 256, 0, st>>>(totals);
+            k_rs_scatter<false><<<tiles, RS_THREADS, RS_SCATTER_SMEM, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, shift,
+                                                                           t.hist, totals, tiles, n_dev);
+            h->last_launches += 4;
+            src ^= 1;
+        }
+    }
+    else
+    {
+        unsigned int* ghist = t.desc + (size_t)RS_PASSES * tiles * 256;
+        unsigned int* tickets = ghist + RS_PASSES * 256;
+        NB_CUDA(cudaMemsetAsync(t.desc, 0, t.desc_words * sizeof(unsigned int), st));
+        k_rs_hist_all<<<h->sm_count * 4, 256, 0, st>>>(t.keys[src], n, n_dev, ghist);
+        k_rs_scan_all<<<1, 256, 0, st>>>(ghist);
+        h->last_launches += 2;
+        for (int pass = 0; pass < RS_PASSES; ++pass)
+        {
+            k_rs_scatter<true><<<tiles, RS_THREADS, RS_SCATTER_SMEM, st>>>(t.keys[src], t.vals[src], t.keys[src ^ 1], t.vals[src ^ 1], n, 8 * pass,
+                                                                          nullptr, ghist + pass * 256, tiles, n_dev,
+                                                                          t.desc + (size_t)pass * tiles * 256, tickets + pass);
+            ++h->last_launches;
+            src ^= 1;
+        }
     }
     t.cur = src;
     NB_CUDA(cudaGetLastError());
@@ -1429,7 +1545,10 @@ int preload_tree()
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_hist)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_rows)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_totals)));
-    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter<false>)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter<true>)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_hist_all)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_all)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_karras)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_bottom_up)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_build_up)));

@@ -469,7 +469,7 @@ def test_graph_replay_of_small_steps_is_bitwise_the_direct_launches(pkg, n):
     assert launches > 300          # 10 steps x ~40 kernels are counted either way
 
 
-def test_agglomerative_build_gives_the_same_tree_and_forces(pkg):
+def test_alternative_build_kernels_give_the_same_tree_and_forces(pkg):
     """NB_BUILD=agglomerative (k_build_up: construction fused with the reduction, nodes numbered by split position)
     must produce the tree of the default two-pass build: same topology through nb_get_tree's renumbering, same node
     sums, bitwise the same accelerations.  Runs in a child process because the switch is read once per process."""
@@ -493,8 +493,9 @@ sim.step(0.02 / 60, 5)
 print(json.dumps({"tree_and_acc": h.hexdigest(), "state": sim.state_hash()}))
 """ % ROOT
     out = []
-    for build in ("karras", "agglomerative"):
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, NB_BUILD=build))
+    # also the alternative sort (one histogram pass + decoupled look-back) and the global-atomic reduction
+    for env in ({}, {"NB_BUILD": "agglomerative"}, {"NB_SORT": "onesweep"}, {"NB_REDUCE": "global"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=dict(os.environ, **env))
         assert r.returncode == 0, r.stderr[-2000:]
         out.append(json.loads(r.stdout.strip().splitlines()[-1]))
-    assert out[0] == out[1]
+    assert all(o == out[0] for o in out[1:])
