@@ -42,6 +42,8 @@ WORKLOADS = {
                           desc="all-pairs fp32 N=262144 single spiral galaxy (GalaxySeeder seed 42), kick-drift dt=0.01"),
     "allpairs_16m": dict(mode="allpairs", n=1 << 24, dt=0.01, seed=42, golden="bh_bh16m_sampled.npz",
                          desc="all-pairs fp32 N=16777216 single spiral galaxy sharded over ranks, positions exchanged every step"),
+    "bh_4k": dict(mode="bh", n=4000, dt=0.02 / 60, seed=42, theta=0.5,
+                  desc="Barnes-Hut theta=0.5 N=4000 (the low end of the reference's interactive range; its default is 1000, SimulationState.hpp:69), per-step LBVH rebuild, dt=0.02/60"),
     "bh_50k": dict(mode="bh", n=50000, dt=0.02 / 60, seed=42, theta=0.5,
                    desc="Barnes-Hut theta=0.5 N=50000 (the reference UI's particle cap), per-step LBVH rebuild, dt=0.02/60"),
     "bh_1m": dict(mode="bh", n=1 << 20, dt=0.02 / 60, seed=42, theta=0.5,
@@ -69,8 +71,8 @@ COLLISION = dict(separation=2000.0, approach_speed=2e16)     # the scene of test
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
 # `ncu --set full` captures (1 GPU); only quoted for the exact workload they were taken on.
 NCU_TRAFFIC = {
-    ("allpairs_1m", 1): (46.866432e6 + 281.826304e6, "profiles/r1_allpairs_fold2_ncu_full.txt"),
-    ("bh_16m", 1): (2.639446e9 + 1.037880e9, "profiles/r1_bh_16m_ncu_full.txt"),
+    ("allpairs_1m", 1): (48.300288e6 + 281.225984e6, "profiles/r2_allpairs_ncu_full.txt"),
+    ("bh_16m", 1): (2.576252e9 + 1.016920e9, "profiles/r2_walk_ncu_full.txt (first steps, all 2^24 bodies inside the root cube)"),
 }
 
 FLOPS_PER_INTERACTION = 20   # 3 sub, 5 d^2, 1 add S, 1 sqrt, 1 div, 3 div, 3 mul, 3 add
@@ -690,6 +692,8 @@ def secondary_plan(args, world):
     if args.secondary != "auto":
         return [(w, max(args.steps, 200) if WORKLOADS[w]["mode"] == "bh" else args.steps, 3) for w in args.secondary.split(",") if w]
     plan = [("bh_16m", 200, 5), ("bh_50k", 2000, 10)]
+    if world == 1:
+        plan.append(("bh_4k", 4000, 10))          # the reference's interactive range (UI.cpp:75 caps N at 50 000)
     if world >= 2:
         # configs[2]: 13.7 s per step on 8 GPUs, 110 s on 2 -- one timed step (two on 8 GPUs) after one untimed step
         plan.append(("allpairs_16m", 2 if world >= 8 else 1, 1))

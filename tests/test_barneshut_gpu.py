@@ -123,7 +123,8 @@ def test_accelerations_match_reference_theta_half(pkg, galaxy):
     print("BH theta=0.5 n=1024 rel err: median %.2e p99 %.2e max %.2e" % (np.median(err), np.quantile(err, 0.99), err.max()))
     assert np.median(err) < BH_MEDIAN_RTOL
     assert np.quantile(err, 0.99) < 1e-2
-    # identical acceptance decisions => identical pair-evaluation count
+    # the same per-body acceptance rule => the same pair-evaluation count, up to cells right at width / r = theta
+    # (the reference accumulates a cell's centre in fp32, this engine in fp64): within 0.2 %
     stats = sim.walk_stats()
     assert abs(stats["leaf_evals"] - int(g["work"][1])) <= 2e-3 * int(g["work"][1])
     sim.close()
