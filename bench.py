@@ -282,6 +282,16 @@ class Ctx:
         self.stream = torch.cuda.Stream()
         torch.cuda.set_stream(self.stream)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+        # what the flush itself costs (it sits inside every timed region): reported beside each result
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for _ in range(3):
+            self.flush.zero_()
+        ev[0].record(self.stream)
+        for _ in range(10):
+            self.flush.zero_()
+        ev[1].record(self.stream)
+        torch.cuda.synchronize()
+        self.flush_ms = ev[0].elapsed_time(ev[1]) / 10.0
 
     def barrier(self):
         if self.world > 1:
@@ -590,6 +600,7 @@ def run_workload(ctx, name, steps, warmup, headline):
         "config": {"workload": wl["desc"], "name": name, "bodies": n, "dt": dt,
                    "parallelism": f"target-sharded x{world}" + (f", exchange={args.exchange}" if world > 1 else ""),
                    "l2": "256 MiB memset between timed steps (inside the timed region); sources (16 B/body) are re-read from L2 by design",
+                   "l2_flush_ms_per_step": ctx.flush_ms,
                    "kernel_variant": args.variant, "seeded_on": seeded_on, "seed_and_init_s": t_seed},
         "gpu_launches": launches,
     }
