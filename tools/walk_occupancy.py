@@ -1,16 +1,25 @@
-import importlib, sys, numpy as np
-sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Lane occupancy of the Barnes-Hut walk (nb_get_walk_occupancy): how many of a warp's 32 lanes are awake per node
+visit, and how much of the walk's issue time the sparse visits take."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("procedural-universe_b200")
-for n in (1 << 20, 1 << 24):
-    p = pkg.seed_galaxy_host(n, 42, 1.0)
+for n in [int(x) for x in sys.argv[1:]] or [1 << 20, 1 << 24]:
     sim = pkg.Sim(mode=pkg.MODE_BARNESHUT, theta=0.5)
-    sim.init(p)
+    sim.seed_galaxy_device(n, 42, 1.0)
     st = sim.walk_stats()
     h = sim.walk_occupancy().astype(np.float64)
     it = h.sum()
-    print("n", n, st, "warp iterations", it, "per warp", it / (n / 32))
-    print(" lane-slots busy %.3f" % ((h * np.arange(33)).sum() / (32 * it)))
+    k = np.arange(33)
+    print("n", n, st, "warp visits", it, "per warp", it / (n / 32))
+    print(" lane slots awake %.3f" % ((h * k).sum() / (32 * it)))
     c = np.cumsum(h) / it
-    for k in (0, 1, 2, 4, 8, 16, 24, 31, 32):
-        print("  <=%2d lanes: %.3f of iterations" % (k, c[k]))
+    lanes = np.cumsum(h * k) / (h * k).sum()
+    for q in (1, 2, 4, 8, 16, 24, 31, 32):
+        print("  <=%2d lanes awake: %.3f of the visits, %.3f of the awake lane-visits (%.1f per lane)" % (q, c[q], lanes[q], np.cumsum(h * k)[q] / n))
     sim.close()
