@@ -187,3 +187,28 @@ def test_mass_scaling_and_step_timers(pkg):
     assert k == 4 and kp == 3 and 0 < kernel_ms < period_ms and 0 < build_ms < period_ms
     a.close()
     b.close()
+
+
+def test_bench_line_on_the_gpu_carries_the_contract_keys():
+    """bench.py on a small workload: ONE JSON line with roofline, cpu_baseline, e2e (host buffers, copies counted),
+    clocks, parity against the oracle, and a secondary workload with its own roofline / parity."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "allpairs_256k", "--steps", "3", "--warmup", "3",
+           "--secondary", "bh_50k"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "gpu_launches", "roofline", "e2e", "clocks", "parity", "cpu_baseline", "secondary"):
+        assert key in d, key
+    assert d["gpu_launches"] >= 6 and d["vs_baseline"] is None and "workload" in d["config"]
+    rf = d["roofline"]
+    assert rf["bound"] == "fp32" and 0.3 < rf["frac"] < 1.0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["unit"] == "TFLOP/s"
+    assert d["e2e"]["h2d_bytes_per_step"] == (1 << 18) * 104 and d["e2e"]["d2h_bytes_per_step"] == (1 << 18) * 104
+    assert 0 < d["e2e"]["value"] <= d["value"] * 1.05
+    assert d["parity"]["live_checker"]["max_rel_err"] < 1e-5 and d["parity"]["device_direct"]["max_rel_err"] < 1e-5
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    s = d["secondary"]["bh_50k"]
+    assert "error" not in s and s["roofline"]["build"]["bound"] == "hbm" and s["parity"]["live_checker"]["median_rel_err"] < 1e-3
+    assert s["clocks"]["samples"] >= 1 and s["interactions_per_step"]["before_timed_steps"]["bodies_inside_root_cube"] == 50000
