@@ -244,6 +244,10 @@ NB_API int nb_get_walk_stats(nb_handle h, uint64_t stats3[3]);
  * hist33[k] = warp iterations (node visits by a warp) during which k of the 32 lanes were at work
  * (the others were parked inside a subtree they had accepted as a whole). */
 NB_API int nb_get_walk_occupancy(nb_handle h, uint64_t hist33[33]);
+/* Of the same instrumented walk: how the visits with few lanes awake are spread over a warp's lanes.  out7 =
+ * {sum, max-per-warp summed over warps} of the per-lane counts of visits with <= 4, <= 8, <= 16 lanes awake, then the
+ * number of warps.  max / (sum / 32) is the imbalance a per-lane treatment of those visits would meet. */
+NB_API int nb_get_walk_sparse_load(nb_handle h, uint64_t out7[7]);
 /* Kinetic and potential energy of the conserved quantity of this force law,
  * E = sum 1/2 m v^2 + position_scale * sum_{i<j} U(r), U = -(G ma mb / sqrt(S)) atan(sqrt(S)/r),
  * potential by exact pair sum over owned targets x all sources (O(N^2/world)). */

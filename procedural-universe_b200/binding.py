@@ -115,6 +115,7 @@ def load():
     L.nb_get_morton.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_get_tree.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(sz)]
     L.nb_get_walk_stats.argtypes = [vp, vp]
+    L.nb_get_walk_sparse_load.argtypes = [vp, vp]
     L.nb_get_walk_occupancy.argtypes = [vp, vp]
     L.nb_get_leaf_cells.argtypes = [vp, vp, vp, C.POINTER(sz)]
     L.nb_energy.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
@@ -388,6 +389,11 @@ class Sim:
         h = (C.c_uint64 * 33)()
         _check(self._L.nb_get_walk_occupancy(self._h, h))
         return np.array(list(h), dtype=np.uint64)
+
+    def walk_sparse_load(self):
+        out = np.zeros(7, dtype=np.uint64)
+        _check(self._L.nb_get_walk_sparse_load(self._h, out.ctypes.data))
+        return out
 
     def energy(self):
         ke, pe = C.c_double(), C.c_double()

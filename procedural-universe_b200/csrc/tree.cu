@@ -38,7 +38,7 @@ namespace nb
 constexpr int kLevels = 21;
 constexpr unsigned long long kOutside = 0xFFFFFFFFFFFFFFFFull;
 constexpr int kEnd = -1;
-constexpr int kWalkStatWords = 3 + 33;   // {cells, pairs, visits} + lane-occupancy histogram [0..32]
+constexpr int kWalkStatWords = 3 + 33 + 8;   // {cells, pairs, visits} + lane-occupancy histogram [0..32] + sparse-visit load per warp: {sum, max} x K = 4, 8, 16 + warps + spare
 
 // counters[] slots
 enum { C_INBOUNDS = 0, C_TOTAL = 1, C_SEG = 2, C_SEG_OOB = 3, C_ROOT = 4, C_WORDS = 8 };   // C_SEG: bodies this rank sorts (sharded sort), C_SEG_OOB: of which outside the cube
@@ -928,6 +928,7 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
     int parked = valid ? 0 : 0x7fffffff;   // the lane is idle while cur < parked; lanes without a target never wake
     float ax = 0.f, ay = 0.f, az = 0.f;
     unsigned int n_cells = 0, n_leaves = 0, n_visits = 0;
+    unsigned int n_sparse4 = 0, n_sparse8 = 0, n_sparse16 = 0;   // STATS: this lane's visits with <= 4 / 8 / 16 lanes of the warp awake
     for (;;)
     {
         const bool live = cur < total;
@@ -964,6 +965,11 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
             // lane-occupancy histogram of the walk: stats[3 + k] counts warp iterations with k lanes at work
             const unsigned int busy = __ballot_sync(0xffffffffu, active);
             if ((threadIdx.x & 31) == 0) atomicAdd(&stats[3 + __popc(busy)], 1ull);
+            if (active)
+            {
+                const int awake = __popc(busy);
+                n_sparse4 += awake <= 4; n_sparse8 += awake <= 8; n_sparse16 += awake <= 16;
+            }
         }
         if (STATS && active)
         {
@@ -1013,6 +1019,16 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
             v += __shfl_down_sync(0xffffffffu, v, o);
         }
         if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[0], c); atomicAdd(&stats[1], l); atomicAdd(&stats[2], v); }
+        // how evenly the sparse visits are spread over the lanes of a warp: sum and max per warp (a per-lane treatment
+        // of those visits would run as long as the busiest lane)
+        const unsigned int sp[3] = {n_sparse4, n_sparse8, n_sparse16};
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const unsigned int sum = __reduce_add_sync(0xffffffffu, sp[k]), mx = __reduce_max_sync(0xffffffffu, sp[k]);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[36 + 2 * k], (unsigned long long)sum); atomicAdd(&stats[37 + 2 * k], (unsigned long long)mx); }
+        }
+        if ((threadIdx.x & 31) == 0) atomicAdd(&stats[42], 1ull);
     }
 }
 
@@ -1709,6 +1725,19 @@ int nb_get_walk_occupancy(nb_handle h, uint64_t hist33[33])
     unsigned long long s[kWalkStatWords];
     NB_CUDA(cudaMemcpy(s, h->tree.stats, sizeof(s), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 33; ++k) hist33[k] = s[3 + k];
+    return NB_OK;
+}
+
+int nb_get_walk_sparse_load(nb_handle h, uint64_t out7[7])
+{
+    NB_REQUIRE(h != nullptr && out7 != nullptr, NB_ERR_ARG, "null argument");
+    NB_REQUIRE(h->cfg.mode == NB_MODE_BARNESHUT, NB_ERR_STATE, "handle is not in Barnes-Hut mode");
+    NB_REQUIRE(h->n > 0, NB_ERR_STATE, "not initialised");
+    NB_CUDA(cudaSetDevice(h->cfg.device));
+    NB_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned long long s[kWalkStatWords];
+    NB_CUDA(cudaMemcpy(s, h->tree.stats, sizeof(s), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 7; ++k) out7[k] = s[36 + k];
     return NB_OK;
 }
 

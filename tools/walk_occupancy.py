@@ -22,4 +22,9 @@ for n in [int(x) for x in sys.argv[1:]] or [1 << 20, 1 << 24]:
     lanes = np.cumsum(h * k) / (h * k).sum()
     for q in (1, 2, 4, 8, 16, 24, 31, 32):
         print("  <=%2d lanes awake: %.3f of the visits, %.3f of the awake lane-visits (%.1f per lane)" % (q, c[q], lanes[q], np.cumsum(h * k)[q] / n))
+    sp = sim.walk_sparse_load().astype(np.float64)
+    for i, q in enumerate((4, 8, 16)):
+        total, mx, warps = sp[2 * i], sp[2 * i + 1], sp[6]
+        print("  visits with <=%2d lanes awake: %.1f per lane on average, busiest lane of a warp %.1f on average (imbalance %.2f)"
+              % (q, total / (32 * warps), mx / warps, mx / (total / 32)))
     sim.close()
