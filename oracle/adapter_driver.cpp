@@ -7,6 +7,7 @@
 // SimulationState.cpp:52-53, 218-227), so the parity test reads like the reference's usage.
 #include <cstdint>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <iostream>
@@ -95,6 +96,39 @@ extern "C"
         if (impl == 1) static_cast<B200Sim*>(sim.get())->Shutdown();
         sim.release();   // never destroy a reference sim on glibc (~CThreadPool deadlocks)
         return 0;
+    }
+
+    // SimulationState::RunBenchmark's protocol (SimulationState.cpp:334-362) for ONE sim: create it through the
+    // factory, Init, then `frames` x Update(1.0f) timed with a steady clock; returns ms per frame (< 0 on failure).
+    // workers: pool size of the reference sims (0 = leave the reference's default, hardware_concurrency() - 1).
+    double adapter_benchmark(void* aos, size_t n, int impl, int type, int frames, int workers, float theta, float dt)
+    {
+        std::vector<Particle> particles(n);
+        std::memcpy(static_cast<void*>(particles.data()), aos, n * sizeof(Particle));
+        Octree::Theta = theta;
+        std::unique_ptr<INBodySim> sim;
+        {
+            Quiet q;
+            sim = impl == 0 ? CreateNBodySim(nullptr, static_cast<ENBodySim>(type))
+                            : CreateB200NBodySim(nullptr, static_cast<ENBodySim>(type));
+        }
+        if (!sim) return -1.0;
+        if (impl == 0 && workers > 0)
+        {
+            if (type == 0) static_cast<BruteForceCPU*>(sim.get())->Pool.SetNumWorkers(workers);
+            if (type == 2) static_cast<BarnesHut*>(sim.get())->Pool.SetNumWorkers(workers);
+        }
+        {
+            FloatEventData ev(theta);
+            EventStream::Report(EEvent::BHThetaChanged, ev);
+        }
+        sim->Init(particles);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int f = 0; f < frames; ++f) sim->Update(dt);   // RunBenchmark passes 1.0f
+        const auto t1 = std::chrono::steady_clock::now();
+        if (impl == 1) static_cast<B200Sim*>(sim.get())->Shutdown();
+        sim.release();   // never destroy a reference sim on glibc (~CThreadPool deadlocks)
+        return std::chrono::duration<double, std::milli>(t1 - t0).count() / frames;
     }
 
     // Sim->RenderDebug(view, proj) through the interface (SimulationState.cpp:81) after `steps` Updates,

@@ -421,6 +421,110 @@ k_rs_scatter(const unsigned long long* __restrict__ keys_in, const unsigned int*
     }
 }
 
+// Small scenes (n <= RS_TILE, the reference's interactive range -- its default is 1 000 bodies): all eight passes in
+// ONE block.  The tile lives in shared memory, ping-ponging between two buffers; a pass ranks exactly as
+// k_rs_scatter does, and for a single tile the digit-ordered slot IS the output position.  Replaces 32 launches.
+constexpr size_t RS_SMALL_SMEM = 2 * RS_TILE * (sizeof(unsigned long long) + sizeof(unsigned int)) + RS_TILE * sizeof(unsigned short) +
+                                 (RS_WARPS + 1) * 256 * sizeof(unsigned int);
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_small(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+           unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int n)
+{
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    unsigned long long* kbuf0 = reinterpret_cast<unsigned long long*>(rs_smem);
+    unsigned long long* kbuf1 = kbuf0 + RS_TILE;
+    unsigned int* vbuf0 = reinterpret_cast<unsigned int*>(kbuf1 + RS_TILE);
+    unsigned int* vbuf1 = vbuf0 + RS_TILE;
+    unsigned int (*wh)[256] = reinterpret_cast<unsigned int (*)[256]>(vbuf1 + RS_TILE);   // [RS_WARPS][256]
+    unsigned int* lbase = &wh[RS_WARPS][0];
+    unsigned short* perm = reinterpret_cast<unsigned short*>(lbase + 256);
+    __shared__ unsigned int warp_tot[RS_WARPS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wbase = warp * (RS_ITEMS * 32);
+    const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const int ip = wbase + r * 32 + lane;
+        kbuf0[ip] = ip < n ? keys_in[ip] : 0ull;
+        vbuf0[ip] = ip < n ? vals_in[ip] : 0u;
+    }
+    for (int pass = 0; pass < 8; ++pass)
+    {
+        const unsigned long long* skeys = (pass & 1) ? kbuf1 : kbuf0;
+        const unsigned int* svals = (pass & 1) ? vbuf1 : vbuf0;
+        unsigned long long* okeys = (pass & 1) ? kbuf0 : kbuf1;
+        unsigned int* ovals = (pass & 1) ? vbuf0 : vbuf1;
+        const int shift = 8 * pass;
+        for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wh[0][0])[k] = 0;
+        __syncthreads();
+        unsigned int packed[RS_ITEMS];               // digit << 16 | rank among the warp's earlier keys of that digit
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r)
+        {
+            const int ip = wbase + r * 32 + lane;
+            const bool ok = ip < n;
+            const unsigned int d = ok ? ((unsigned int)(skeys[ip] >> shift) & 255u) : (256u + lane);
+            const unsigned int peers = __match_any_sync(0xffffffffu, d);
+            const unsigned int before = ok ? wh[warp][d] : 0u;
+            __syncwarp();
+            packed[r] = (d << 16) | (before + __popc(peers & lt));
+            if (ok && lane == __ffs(peers) - 1) wh[warp][d] = before + __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            const int d = threadIdx.x;
+            unsigned int run = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) { const unsigned int c = wh[w][d]; wh[w][d] = run; run += c; }
+            unsigned int x = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) warp_tot[warp] = x;
+            __syncthreads();
+            unsigned int wprefix = 0;
+            for (int w = 0; w < warp; ++w) wprefix += warp_tot[w];
+            lbase[d] = wprefix + x - run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r)
+        {
+            const int ip = wbase + r * 32 + lane;
+            if (ip < n)
+            {
+                const unsigned int d = packed[r] >> 16;
+                perm[lbase[d] + wh[warp][d] + (packed[r] & 0xffffu)] = (unsigned short)ip;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RS_ITEMS; ++k)
+        {
+            const int slot = k * RS_THREADS + threadIdx.x;
+            if (slot < n)
+            {
+                const int ip = perm[slot];
+                okeys[slot] = skeys[ip];
+                ovals[slot] = svals[ip];
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += RS_THREADS)
+    {
+        keys_out[i] = kbuf0[i];                       // eight passes: the result is back in the first buffer
+        vals_out[i] = vbuf0[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: Karras radix tree (HPG 2012, section 3) over the m sorted in-bounds keys.
 // Node ids: internal node i -> i, leaf slot j -> leaf_base + j.
@@ -1310,6 +1414,7 @@ int tree_reserve(nb_sim* h)
     {
         NB_CUDA(cudaFuncSetAttribute(k_rs_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
         NB_CUDA(cudaFuncSetAttribute(k_rs_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM));
+        NB_CUDA(cudaFuncSetAttribute(k_rs_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMALL_SMEM));
         if (dev >= 0 && dev < 64) opted_in[dev].store(true, std::memory_order_release);    // idempotent: a second caller repeats it at worst
     }
     if (t.capacity >= n) return NB_OK;
@@ -1379,6 +1484,14 @@ int tree_build(nb_sim* h, bool collective)
         src = 1;
         n_dev = t.counters + C_SEG;
     }
+    if (!sharded && n <= RS_TILE)
+    {
+        k_rs_small<<<1, RS_THREADS, RS_SMALL_SMEM, st>>>(t.keys[0], t.vals[0], t.keys[1], t.vals[1], n);
+        ++h->last_launches;
+        src = 1;
+    }
+    else
+    {
     static const bool three_kernel_sort = [] { const char* v = std::getenv("NB_SORT"); return v == nullptr || std::strcmp(v, "onesweep") != 0; }();
     if (three_kernel_sort || (size_t)n >= ((size_t)1 << 30))
     {
@@ -1411,6 +1524,7 @@ int tree_build(nb_sim* h, bool collective)
             ++h->last_launches;
             src ^= 1;
         }
+    }
     }
     t.cur = src;
     NB_CUDA(cudaGetLastError());
@@ -1563,6 +1677,7 @@ int preload_tree()
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_totals)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter<false>)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scatter<true>)));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_small)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_hist_all)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_rs_scan_all)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_karras)));

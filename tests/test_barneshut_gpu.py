@@ -467,7 +467,7 @@ def test_graph_replay_of_small_steps_is_bitwise_the_direct_launches(pkg, n):
         launches = sim.last_step_timing()[2]
         sim.close()
     assert hashes[0] == hashes[1]
-    assert launches > 300          # 10 steps x ~40 kernels are counted either way
+    assert launches >= 100         # 10 steps x (13 kernels with the single-block sort at 4 000 bodies, ~40 at 50 000), counted either way
 
 
 def test_alternative_build_kernels_give_the_same_tree_and_forces(pkg):
