@@ -40,7 +40,10 @@ $(LIB): $(CU_OBJS) $(CPP_OBJS)
 	@mkdir -p $(PKG)/lib
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -ldl -lpthread
 
-tools: tools/tune_allpairs
+tools: tools/tune_allpairs tools/issue_probe
+
+tools/issue_probe: tools/issue_probe.cu
+	$(NVCC) $(ARCH) -O3 -o $@ $<
 
 tools/tune_allpairs: tools/tune_allpairs.cu $(SRC)/allpairs.cuh
 	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ $<
@@ -49,6 +52,6 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(OBJ) $(PKG)/lib $(PKG)/bin tools/tune_allpairs
+	rm -rf $(OBJ) $(PKG)/lib $(PKG)/bin tools/tune_allpairs tools/issue_probe
 
 .PHONY: all tools oracle clean
