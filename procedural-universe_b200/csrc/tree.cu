@@ -1147,15 +1147,19 @@ k_walk(const float4* __restrict__ posw, const unsigned int* __restrict__ order, 
 // measured slower (39.4 ms against 38.5 ms at 16 M bodies).  Measured at 16 M bodies on one B200: 39.2 ms (k_walk),
 // 38.5 ms (this kernel); also tried and rejected: skipping the interaction when no lane uses the record (44.4 ms), and
 // requesting record cur + 1 ahead of the decision (57.9 ms) -- the loop is bound by instruction issue, not by latency.
-template <bool BALANCED, bool LOAD256 = false>
+// TPW (targets per warp) < 32 serves small scenes: with a few thousand bodies the GPU is nearly empty and a warp's
+// walk is a chain of dependent record loads, so fewer targets per warp = a smaller union = a shorter chain, on more
+// warps.  A lane's result does not depend on which targets share its warp, so every TPW gives bitwise the same forces.
+template <bool BALANCED, bool LOAD256 = false, int TPW = 32>
 __global__ void __launch_bounds__(256)
 k_walk2(const float4* __restrict__ posw, const unsigned int* __restrict__ order, const unsigned int* __restrict__ tlist,
         int ntargets, const unsigned int* __restrict__ counters, const float4* __restrict__ nodes,
         int first, int count, float sc, double* __restrict__ acc, AccTable owners)
 {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = BALANCED ? (blockIdx.x * owners.world + owners.rank) * 256 + threadIdx.x
-                           : blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t < ntargets;
+                           : (TPW == 32 ? gt : (gt >> 5) * TPW + (gt & 31));
+    const bool valid = t < ntargets && (TPW == 32 || (gt & 31) < TPW);
     unsigned int body = 0;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid)
@@ -1654,6 +1658,12 @@ int tree_walk(nb_sim* h, bool balanced, bool g_walk_stats)
     else if (h->cfg.kernel_variant == 5)      // one 256-bit load per record (measured: 39.4 ms against 38.5 ms at 16 M bodies)
         k_walk2<false, true><<<blocks, 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, (int)h->count, sc,
                                                     h->acc, owners);
+    else if (group == 32 && ntargets < 20000)       // 2 targets per warp
+        k_walk2<false, false, 2><<<blocks_for((size_t)((ntargets + 1) / 2) * 32, 256), 256, 0, st>>>(
+            h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, (int)h->count, sc, h->acc, owners);
+    else if (group == 32 && ntargets < 150000)      // 8 targets per warp
+        k_walk2<false, false, 8><<<blocks_for((size_t)((ntargets + 7) / 8) * 32, 256), 256, 0, st>>>(
+            h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, (int)h->count, sc, h->acc, owners);
     else if (group == 32)
         k_walk2<false><<<blocks, 256, 0, st>>>(h->posw, order, tlist, ntargets, t.counters, t.walk_a, (int)h->first, (int)h->count, sc,
                                               h->acc, owners);
@@ -1695,6 +1705,8 @@ int preload_tree()
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk2<false>))));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk2<true>))));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk2<false, true>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk2<false, false, 2>))));
+    NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk2<false, false, 8>))));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>((k_walk<false, 32, false, true>))));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_leaf_cells)));
     NB_CUDA(cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k_select_flags)));
