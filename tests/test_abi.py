@@ -39,6 +39,23 @@ def test_bad_arguments_are_rejected(pkg):
     assert lib.nb_step(None, 0.01, 1) == -1
     buf = np.zeros(10, dtype=pkg.PARTICLE_DTYPE)
     assert lib.nb_seed_galaxy_host(buf.ctypes.data, 10, 100, 1, 1.0) == -1      # stride < 104
+    # the device seeders validate before they touch the GPU
+    assert lib.nb_seed_device(pkg.SEEDER_GALAXY, 0, buf.ctypes.data, 10, 100, 1, None) == -1          # stride < 104
+    assert lib.nb_seed_device(7, 0, buf.ctypes.data, 10, 104, 1, None) == -1 and b"unknown seeder" in lib.nb_last_error()
+    assert lib.nb_seed_device(pkg.SEEDER_STARSYSTEM, 0, buf.ctypes.data, 0, 104, 1, None) == -1
+    assert lib.nb_seed_device(pkg.SEEDER_GALAXY, 0, None, 10, 104, 1, None) == -1
+    assert lib.nb_seed_device(pkg.SEEDER_GALAXY, 0, None, 0, 104, 1, None) == 0                       # nothing to seed
+    for fn in (lib.nb_get_accel_of, lib.nb_get_step_accel_of, lib.nb_direct_accel):
+        assert fn(None, None, 0, None) == -1
+    assert lib.nb_state_hash(None, None) == -1 and lib.nb_scale_masses(None, 2.0) == -1 and lib.nb_enable_graphs(None, 1) == -1
+
+
+def test_no_gpu_the_device_seeder_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.NBodyError):
+        pkg.seed_device(pkg.SEEDER_GALAXY, 100, 1)
 
 
 def test_no_gpu_means_error_not_fallback(pkg):
