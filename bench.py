@@ -701,7 +701,10 @@ def secondary_plan(args, world):
     if args.secondary == "none" or (args.secondary == "auto" and args.workload != "allpairs_1m"):
         return []
     if args.secondary != "auto":
-        return [(w, max(args.steps, 200) if WORKLOADS[w]["mode"] == "bh" else args.steps, 3) for w in args.secondary.split(",") if w]
+        # an explicit list: Barnes-Hut scenes get enough steps for the 100 ms clock sampler (a 50 000-body step is 0.6 ms)
+        long_runs = {"bh_50k": 2000, "bh_4k": 4000}
+        return [(w, max(args.steps, long_runs.get(w, 200)) if WORKLOADS[w]["mode"] == "bh" else args.steps, 3)
+                for w in args.secondary.split(",") if w]
     plan = [("bh_16m", 200, 5), ("bh_50k", 2000, 10)]
     if world == 1:
         plan.append(("bh_4k", 4000, 10))          # the reference's interactive range (UI.cpp:75 caps N at 50 000)
