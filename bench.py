@@ -236,7 +236,8 @@ def run_reference(args, wl):
         "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "steps_per_s": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64 accumulate / f32 geometry", "data": "synthetic",
-        "config": {"workload": wl["desc"], "note": "each step is a bounded sample of the workload; ms_per_step is the sample rate scaled to a whole step"},
+        "config": {"workload": wl["desc"], "name": args.workload, "bodies": n, "dt": wl["dt"],
+                   "note": "each step is a bounded sample of the workload; ms_per_step is the sample rate scaled to a whole step"},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
