@@ -546,6 +546,7 @@ __device__ __forceinline__ int level_of(int prefix_bits)
 // deeper than its parent's).  Written by the parent's thread, which knows both children's ranges and
 // therefore their prefixes; the same thread counts owning nodes per first slot (pre-order ranks).
 constexpr unsigned short kOwns = 0x100;
+constexpr unsigned short kIsLeft = 0x200;     // the node is its parent's LEFT child (same first slot as the parent)
 
 __global__ void __launch_bounds__(256)
 k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ counters, int leaf_base,
@@ -592,7 +593,7 @@ k_karras(const unsigned long long* __restrict__ keys, const unsigned int* __rest
     if (cl < leaf_base)
     {
         const int lc = level_of(delta_fn(keys, m, lo, gamma));
-        meta[cl] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0);
+        meta[cl] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0) | kIsLeft;
         if (lc > level) atomicAdd(&cnt[lo], 1u);
     }
     if (cr < leaf_base)
@@ -846,7 +847,7 @@ k_build_up(const float4* __restrict__ posw, const unsigned int* __restrict__ ord
         if (cl < leaf_base)
         {
             const int lc = level_of(delta_fn(keys, m, l, node));
-            meta[cl] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0);
+            meta[cl] = (unsigned short)lc | (lc > level ? kOwns : (unsigned short)0) | kIsLeft;
             if (lc > level) atomicAdd(&cnt[l], 1u);
         }
         if (cr < leaf_base)
@@ -918,13 +919,15 @@ k_rank(unsigned int* __restrict__ counters, int n, int leaf_base, const int2* __
     if (t < m) rank[leaf_base + t] = t + (int)pref[t + 1];
     if (t < m - 1 && owns_cell(t, meta))
     {
+        // climb while the node is a left child: one dependent pair of loads per level (parent link, then the parent's
+        // meta, which carries both "owns a cell" and whether the climb goes on)
         int above = 0, v = t;
-        for (;;)
+        unsigned short mv = meta[t];
+        while (mv & kIsLeft)
         {
-            const int p = parent[v];
-            if (p == kEnd || child[p].x != v) break;
-            if (owns_cell(p, meta)) ++above;
-            v = p;
+            v = parent[v];
+            mv = meta[v];
+            above += (mv & kOwns) ? 1 : 0;
         }
         const int f = first_slot[t];
         rank[t] = f + (int)pref[f] + above;
