@@ -715,46 +715,21 @@ struct AllPairsKernel
 inline const AllPairsKernel* allpairs_table(int* count)
 {
     static const AllPairsKernel table[] = {
-        NB_AP_ENTRY4(256, 4, 2, 2),                      // index 0 = library default (fastest at 1e-5 parity)
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 4, 2),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 2, 2),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 128, 4, 4),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 128, 2, 4),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 128, 2, 6),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 2, 3),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 512, 2, 1),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 512, 4, 1),
-        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 256, 4, 2),
-        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 256, 8, 2),
-        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 128, 4, 4),
-        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 128, 8, 4),
-        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 256, 4, 3),
-        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 512, 4, 1),
-        NB_AP_ENTRY(k_allpairs_scalar, 0, 256, 4, 2),
-        NB_AP_ENTRY(k_allpairs_scalar, 0, 256, 2, 3),
-        NB_AP_ENTRY(k_allpairs_scalar, 0, 128, 4, 4),
-        NB_AP_ENTRY(k_allpairs_scalar, 0, 256, 8, 2),
-        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 2, 2),      // 18
-        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 4, 2),
-        NB_AP_ENTRY(k_allpairs_fold, 3, 128, 2, 4),
-        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 2, 3),
-        NB_AP_ENTRY(k_allpairs_fold, 3, 512, 2, 1),
-        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 1, 4),
-        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 1, 4),
-        NB_AP_ENTRY4(256, 2, 2, 2),                      // 25
-        NB_AP_ENTRY4(256, 4, 2, 1),
-        NB_AP_ENTRY4(256, 4, 2, 2),
-        NB_AP_ENTRY4(256, 3, 2, 2),
-        NB_AP_ENTRY4(128, 4, 4, 1),
-        NB_AP_ENTRY4(128, 4, 4, 2),                      // 30
-        NB_AP_ENTRY4(256, 6, 1, 1),
-        NB_AP_ENTRY4(256, 8, 1, 1),
-        NB_AP_ENTRY4(512, 4, 1, 1),
-        NB_AP_ENTRY4(256, 2, 3, 2),
-        NB_AP_ENTRY4(384, 4, 1, 1),                      // 35
-        NB_AP_ENTRY4(128, 6, 3, 1),
-        NB_AP_ENTRY5(256, 4, 2, 2, 8),                   // 37: scalar accumulations (50.2 TFLOP/s against 51.0 packed)
-        NB_AP_ENTRY5(256, 4, 2, 2, 15),                  // 38: all scalar (45.9): every mix of scalar and packed groups is slower than all packed
+        // index 0 = library default (fastest at 1e-5 parity).  The round-1 tuning sweep covered 38 entries
+        // (profiles/r1_tune_sweep_a.txt); what stays is one representative per kernel family and the neighbours
+        // of the default in (threads, targets per thread, blocks per SM, unroll), all kept under test.
+        NB_AP_ENTRY4(256, 4, 2, 2),                      // 0
+        NB_AP_ENTRY(k_allpairs_scalar, 0, 256, 4, 2),    // 1: scalar FFMA, weight multiplied in: 56 % of peak
+        NB_AP_ENTRY(k_allpairs_srcpair, 1, 256, 4, 2),   // 2: packed over source pairs, 13 ops: 65.7 %
+        NB_AP_ENTRY(k_allpairs_tgtpair, 2, 256, 4, 2),   // 3: packed over target pairs
+        NB_AP_ENTRY(k_allpairs_fold, 3, 256, 4, 2),      // 4: weight folded under the rsqrt: 68.6 %
+        NB_AP_ENTRY4(256, 2, 2, 2),                      // 5
+        NB_AP_ENTRY4(256, 4, 2, 1),                      // 6
+        NB_AP_ENTRY4(128, 4, 4, 2),                      // 7
+        NB_AP_ENTRY4(256, 6, 1, 1),                      // 8
+        NB_AP_ENTRY4(256, 8, 1, 1),                      // 9
+        NB_AP_ENTRY5(256, 4, 2, 2, 8),                   // 10: scalar accumulations (50.2 TFLOP/s against 51.0 packed at 256 K bodies)
+        NB_AP_ENTRY5(256, 4, 2, 2, 15),                  // 11: all scalar (45.9): every mix of scalar and packed groups is slower than all packed
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

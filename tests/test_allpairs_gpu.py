@@ -36,7 +36,7 @@ def test_accelerations_match_reference_n4096(pkg, galaxy4096):
 def test_every_kernel_variant_matches(pkg):
     p = pkg.seed_galaxy_host(3000, 11, 1.0)            # ragged: not a multiple of any tile
     want = checker.allpairs_accel(p)
-    for variant in range(38):
+    for variant in range(12):
         sim = pkg.Sim(mode=pkg.MODE_ALLPAIRS, kernel_variant=variant)
         sim.init(p)
         err = rel_err(sim.accelerations(), want)
